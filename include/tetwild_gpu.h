@@ -1,0 +1,133 @@
+/*
+ * tetwild_gpu.h -- C ABI of libtetwild_gpu.so: TetWild's data-parallel hot path on NVIDIA B200 (sm_100a).
+ *
+ * The reference (Yixin-Hu/TetWild @49de8cd) has no plugin/FFI layer for this path except one true C ABI, the ISPC
+ * operator energy_ispc (src/ispc/energy.ispc:7-21). This header is the boundary a maintainer binds instead of:
+ *
+ *   S1  ispc::energy_ispc(V1_x..V4_z, E, count)                   src/ispc/energy.ispc:7-21, LocalOperations.h:21-23
+ *   S2  GEO::MeshFacetsAABBWithEps (ctor, nearest_facet,          src/tetwild/geogram/mesh_AABB.h:77,130,162,182,199,221
+ *       facet_in_envelope[_with_hint], squared_distance)
+ *   S3  LocalOperations::isFaceOutEnvelop / isPointOutEnvelop /   src/tetwild/LocalOperations.h:69,97-100,109-111
+ *       calTetQualities / comformalAMIPS{Energy,Jacobian,Hessian}_new,
+ *       VertexSmoother::NewtonsUpdate / getNewEnergy              src/tetwild/VertexSmoother.cpp:627-702, :544-625
+ *   S4  igl::winding_number(V,F,O,W) + the W > 0.5 rule           src/tetwild/InoutFiltering.cpp:45-75,
+ *                                                                 src/tetwild/MeshRefinement.cpp:614,1056
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, a cudaError_t value or a TWG_ERR_* code
+ *     otherwise, never throws; twg_last_error() gives the message. There is NO CPU fallback: if no sm_100-class
+ *     device can be opened twg_create fails.
+ *   - functions without suffix take HOST buffers (caller-owned; pageable or pinned) and include the host<->device
+ *     copies; functions ending in _dev take DEVICE pointers on the context's device plus a cudaStream_t (as void*,
+ *     NULL = the context's stream) and are asynchronous on that stream.
+ *   - vertices are xyz-interleaved doubles, facet / tet indices are 32-bit, facet ids returned are in the CALLER's
+ *     numbering (the library sorts facets internally, like mesh_reorder at mesh_AABB.cpp:368-370, but never
+ *     mutates caller data).
+ *   - one context = one device; calls on one context are serialised by the caller (the reference is single-threaded).
+ *     Multi-GPU: one context per device, batches split by index range.
+ */
+#ifndef TETWILD_GPU_H
+#define TETWILD_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TWG_ERR_INTERNAL 10001
+#define TWG_ERR_INVALID_ARG 10002
+#define TWG_ERR_NO_DEVICE 10003
+#define TWG_ERR_ALIGNMENT 10004
+
+#define TWG_MAX_ENERGY 1e50        /* State::MAX_ENERGY, src/tetwild/State.h:29 */
+#define TWG_NO_FACET 0xffffffffu   /* GEO::NO_FACET */
+
+typedef struct twg_ctx twg_ctx;
+typedef struct twg_surface twg_surface;   /* S2: envelope / nearest-facet structure over the input surface */
+typedef struct twg_winding twg_winding;   /* S4: winding-number hierarchy over a (tracked) surface */
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int twg_create(twg_ctx** ctx, int device_id);
+void twg_destroy(twg_ctx* ctx);
+const char* twg_last_error(const twg_ctx* ctx);
+int twg_device(const twg_ctx* ctx);
+int twg_synchronize(twg_ctx* ctx);
+uint64_t twg_launch_count(const twg_ctx* ctx);  /* kernels launched by this context so far */
+const char* twg_version(void);
+
+/* ---- S2: surface build (replaces MeshFacetsAABBWithEps::MeshFacetsAABBWithEps, mesh_AABB.cpp:356-379) ------------ */
+int twg_surface_create(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_surface** out);
+int twg_surface_create_dev(twg_ctx* ctx, const double* dV, uint32_t nV, const uint32_t* dF, uint32_t nF, twg_surface** out);
+void twg_surface_destroy(twg_surface* s);
+uint32_t twg_surface_num_facets(const twg_surface* s);
+
+/* a10/a12: out[i] = 1 iff min_f d2(P_i, f) > eps2
+ * (isPointOutEnvelop LocalOperations.cpp:1034-1044; per-sample test of :1083-1093 via facet_in_envelope_with_hint) */
+int twg_envelope_points_out(twg_surface* s, const double* P, uint64_t n, double eps2, uint8_t* out);
+int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, double eps2, uint8_t* dOut, void* stream);
+
+/* a9: isFaceOutEnvelop(tri) (LocalOperations.cpp:967-976, :1046-1109): tris = n*9 doubles; triangles are sampled on
+ * the device with sampleTriangle semantics (Common.cpp:143-255); out[i] = 1 iff some sample is farther than eps from
+ * the surface; collinear triangles give 0 (:1048). */
+int twg_envelope_faces_out(twg_surface* s, const double* tris, uint64_t n, double sampling_dist, double eps2, uint8_t* out);
+int twg_envelope_faces_out_dev(twg_surface* s, const double* dTris, uint64_t n, double sampling_dist, double eps2,
+                               uint8_t* dOut, void* stream);
+
+/* a13: nearest_facet / squared_distance (mesh_AABB.h:130-141,221-226). Any output pointer may be NULL.
+ * facet ids are unique up to exact distance ties. */
+int twg_nearest(twg_surface* s, const double* P, uint64_t n, uint32_t* facet, double* nearest_xyz, double* d2);
+int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFacet, double* dNearest, double* dD2, void* stream);
+
+/* a8 (debug / parity): the samples sampleTriangle would generate for one triangle, in the reference's order.
+ * Writes at most cap points, *count = number the reference generates. */
+int twg_sample_triangle(twg_ctx* ctx, const double* tri9, double sampling_dist, double* out_xyz, uint64_t cap, uint64_t* count);
+
+/* ---- S1/S3: AMIPS ------------------------------------------------------------------------------------------------ */
+/* S1 mirror: exactly energy_ispc's argument list (12 SoA coordinate arrays, E, count) plus the context. */
+int twg_amips_energy_soa(twg_ctx* ctx, const double* const T[12], double* E, uint64_t n);
+int twg_amips_energy_soa_dev(twg_ctx* ctx, const double* const dT[12], double* dE, uint64_t n, void* stream);
+/* a1+a2+a3 per tet: E[n], J3[n*3], H9[n*9] (row-major 3x3); any of E/J3/H9 may be NULL */
+int twg_amips_ejh_soa(twg_ctx* ctx, const double* const T[12], double* E, double* J3, double* H9, uint64_t n);
+int twg_amips_ejh_soa_dev(twg_ctx* ctx, const double* const dT[12], double* dE, double* dJ3, double* dH9, uint64_t n, void* stream);
+/* a4: calTetQualities / calTetQuality_AMIPS (LocalOperations.cpp:695-773, :862-884): indexed gather, exact
+ * orientation gate, slim_energy = MAX_ENERGY when not POSITIVE / inf / NaN / <= 0 */
+int twg_amips_quality(twg_ctx* ctx, const double* Vxyz, uint32_t nV, const int32_t* tets4, uint64_t nT, double* slim_energy);
+int twg_amips_quality_dev(twg_ctx* ctx, const double* dVxyz, uint32_t nV, const int32_t* dTets4, uint64_t nT, double* dSlim, void* stream);
+/* a5: NewtonsUpdate (VertexSmoother.cpp:627-702) for nGroups one-rings at once. Group g owns members
+ * k in [group_off[g], group_off[g+1]); member k is tet tets4[t_ids ? t_ids[k] : k]; the tet is rotated so that
+ * center[g] sits in slot 0 (:640-651). Outputs E[g], J3[g*3], H9[g*9], ok[g] (0 where the reference returns false:
+ * E NaN / <= 0, J or H not finite; E = MAX_ENERGY where it is +inf, :680-699). ok may be NULL. */
+int twg_amips_ring_ejh(twg_ctx* ctx, const double* Vxyz, uint32_t nV, const int32_t* tets4, uint64_t nT, const int32_t* t_ids,
+                       const uint64_t* group_off, const int32_t* center, uint64_t nGroups, double* E, double* J3, double* H9,
+                       uint8_t* ok);
+int twg_amips_ring_ejh_dev(twg_ctx* ctx, const double* dVxyz, uint32_t nV, const int32_t* dTets4, uint64_t nT,
+                           const int32_t* dTids, const uint64_t* dGroupOff, const int32_t* dCenter, uint64_t nGroups,
+                           double* dE, double* dJ3, double* dH9, uint8_t* dOk, void* stream);
+/* a6: getNewEnergy (VertexSmoother.cpp:544-625): sum of energies over each ring in stored vertex order, clamped to
+ * MAX_ENERGY when inf / NaN / <= 0 / > MAX_ENERGY (:619-622) */
+int twg_amips_ring_energy(twg_ctx* ctx, const double* Vxyz, uint32_t nV, const int32_t* tets4, uint64_t nT, const int32_t* t_ids,
+                          const uint64_t* group_off, uint64_t nGroups, double* E);
+int twg_amips_ring_energy_dev(twg_ctx* ctx, const double* dVxyz, uint32_t nV, const int32_t* dTets4, uint64_t nT,
+                              const int32_t* dTids, const uint64_t* dGroupOff, uint64_t nGroups, double* dE, void* stream);
+
+/* ---- S4: generalized winding number ------------------------------------------------------------------------------ */
+/* F may contain repeated faces (InoutFiltering.cpp:99-100). */
+int twg_winding_create(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out);
+void twg_winding_destroy(twg_winding* w);
+/* W[i] and/or keep[i] = (W[i] > 0.5) for query i (either may be NULL) */
+int twg_winding_eval(twg_winding* w, const double* C, uint64_t nC, double* W, uint8_t* keep);
+int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* dW, uint8_t* dKeep, void* stream);
+/* igl::winding_number(V,F,O,W) one-shot mirror (build + eval + free) */
+int twg_winding_number(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, const double* C,
+                       uint64_t nC, double* W, uint8_t* keep);
+/* InoutFiltering::filter decision (InoutFiltering.cpp:45-75): keep = W > 0.5; if nothing is kept, faces are flipped
+ * (columns 1,2 swapped) and the test repeated; *retried tells which happened */
+int twg_inout_filter(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, const double* C,
+                     uint64_t nC, uint8_t* keep, int* retried);
+/* statistics of the hierarchy: number of nodes, total cap segments, leaf triangles */
+int twg_winding_stats(const twg_winding* w, uint64_t* n_nodes, uint64_t* n_cap_segments, uint64_t* n_triangles);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETWILD_GPU_H */

@@ -1,0 +1,73 @@
+// tests/host_harness.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the __host__ __device__ numeric core of the product (tetwild_b200/csrc/tw_math.cuh, sampling.cuh) as plain
+// C++ so the CPU-only test tier can check the exact source the kernels run (closed-form AMIPS, record-based
+// point-triangle distance, run-decomposed sampleTriangle, exact predicates) against the oracle without a GPU.
+// It is not part of libtetwild_gpu.so and is never used by the product path.
+#include <cstdint>
+#include <cstring>
+#include "../tetwild_b200/csrc/tw_math.cuh"
+#include "../tetwild_b200/csrc/sampling.cuh"
+
+extern "C" {
+
+void hh_amips_ejh(const double* T12, double* E, double* J3, double* H9) {
+    tw::Amips r;
+    tw::amips_eval<true>(T12, r);
+    *E = r.E;
+    for (int k = 0; k < 3; ++k) J3[k] = r.J[k];
+    H9[0] = r.H[0]; H9[1] = r.H[1]; H9[2] = r.H[2];
+    H9[3] = r.H[1]; H9[4] = r.H[3]; H9[5] = r.H[4];
+    H9[6] = r.H[2]; H9[7] = r.H[4]; H9[8] = r.H[5];
+}
+
+void hh_amips_ejh_batch(const double* T /* 12 x n, row-major */, uint64_t n, double* E, double* J3, double* H9) {
+    for (uint64_t i = 0; i < n; ++i) {
+        double x[12];
+        for (int k = 0; k < 12; ++k) x[k] = T[(size_t)k * n + i];
+        hh_amips_ejh(x, E + i, J3 + 3 * i, H9 + 9 * i);
+    }
+}
+
+double hh_amips_energy(const double* T12) {
+    tw::Amips r;
+    tw::amips_eval<false>(T12, r);
+    return r.E;
+}
+
+double hh_tri_sqdist(const double* p, const double* v0, const double* v1, const double* v2, double* nearest) {
+    tw::TriRec r;
+    tw::make_trirec(v0, v1, v2, 0, r);
+    tw::V3 P = tw::mk(p[0], p[1], p[2]);
+    if (r.flags & 1u) {
+        double tv[9];
+        memcpy(tv, v0, 24); memcpy(tv + 3, v1, 24); memcpy(tv + 6, v2, 24);
+        tw::V3 q;
+        double d = tw::tri_sqdist_degenerate(P, tv, q);
+        nearest[0] = q.x; nearest[1] = q.y; nearest[2] = q.z;
+        return d;
+    }
+    double s, t;
+    double d = tw::tri_sqdist_rec(P, r, s, t);
+    tw::V3 q = tw::tri_nearest_point(r, s, t);
+    nearest[0] = q.x; nearest[1] = q.y; nearest[2] = q.z;
+    return d;
+}
+
+struct Sink {
+    double* out; uint64_t cap, n;
+    void operator()(tw::V3 p) { if (n < cap) { out[3 * n] = p.x; out[3 * n + 1] = p.y; out[3 * n + 2] = p.z; } ++n; }
+};
+uint64_t hh_sample_triangle(const double* tri9, double sd, double* out, uint64_t cap) {
+    tw::SamplePlan P;
+    tw::make_plan(tri9, sd, P);
+    Sink s{out, cap, 0};
+    tw::enumerate_samples(P, s);
+    return s.n;
+}
+
+int hh_orient3d(const double* a, const double* b, const double* c, const double* d) { return tw::exact::orient3d(a, b, c, d); }
+int hh_orient3d_exact(const double* a, const double* b, const double* c, const double* d) { return tw::exact::orient3d_exact(a, b, c, d); }
+int hh_cgal_orientation(const double* p, const double* q, const double* r, const double* s) { return tw::exact::cgal_orientation(p, q, r, s); }
+int hh_triangle_is_degenerate(const double* p, const double* q, const double* r) { return tw::exact::triangle_is_degenerate(p, q, r) ? 1 : 0; }
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""GPU tier: envelope / nearest-facet kernels through the C ABI against the oracle. Decisions and squared distances
+are bit exact; facet ids are compared where the minimum is unique."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, unhex
+from tetwild_b200 import synth
+import tetwild_b200 as tw
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def knot(ctx, oracle):
+    V, F = synth.torus_knot(200, 40)
+    return V, F, tw.Surface(ctx, V, F), oracle.Surface(V, F)
+
+
+def test_points_out_exact(knot):
+    V, F, S, OS = knot
+    for eps_rel in (1e-3, 4e-3):
+        sd, eps, eps2 = synth.state_eps(eps_rel)
+        P = synth.envelope_points(V, F, 200000, eps, seed=20240501)
+        got = S.points_out(P, eps2)
+        ref = OS.points_out(P, eps2, threads=4)
+        assert np.array_equal(got, ref)
+        assert 0.2 < got.mean() < 0.8
+    assert np.array_equal(S.points_out(P[:3000], eps2), OS.points_out(P[:3000], eps2, brute=True, threads=4))
+
+
+def test_tree_golden(ctx):
+    g = load_golden("tree_golden.json")
+    V, F = synth.torus_knot(60, 12)
+    S = tw.Surface(ctx, V, F)
+    P = unhex(g["P"], (-1, 3))
+    assert np.array_equal(S.points_out(P, float.fromhex(g["eps2"])), np.array(g["out"], dtype=np.uint8))
+    f, q, d = S.nearest(P)
+    assert np.array_equal(d, unhex(g["nearest_d2"]))
+    same = f == np.array(g["nearest_facet_original_ids"], dtype=np.uint32)
+    assert same.mean() > 0.9
+    assert np.array_equal(q[same], unhex(g["nearest_pt"], (-1, 3))[same])
+
+
+def test_nearest_exact(knot):
+    V, F, S, OS = knot
+    sd, eps, eps2 = synth.state_eps(1e-3)
+    P = synth.envelope_points(V, F, 100000, eps, seed=5)
+    f, q, d = S.nearest(P)
+    fr, qr, dr = OS.nearest(P, threads=4)
+    assert np.array_equal(d, dr)                       # squared_distance(): bit exact
+    same = f == fr
+    assert same.mean() > 0.7                           # ties (points exactly on shared edges) may pick either facet
+    assert np.array_equal(q[same], qr[same])
+    assert np.allclose(((P - q) ** 2).sum(1), d, rtol=1e-6, atol=1e-18)
+    assert np.array_equal(S.squared_distance(P[:1000]), dr[:1000])
+    # isPointOutEnvelop goes through squared_distance() > eps_2 (LocalOperations.cpp:1037): same decision
+    assert np.array_equal((d > eps2).astype(np.uint8), S.points_out(P, eps2))
+
+
+def test_edge_cases(ctx, oracle):
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    for F in (np.array([[0, 1, 2]]), np.array([[0, 1, 2], [0, 1, 3]]), np.array([[0, 1, 2], [0, 1, 3], [1, 2, 3]])):
+        S = tw.Surface(ctx, V, F.astype(np.uint32))
+        OS = oracle.Surface(V, F.astype(np.uint32))
+        P = np.random.default_rng(0).uniform(-0.5, 1.5, size=(5000, 3))
+        P[:100, 2] = 0.0
+        for eps2 in (0.0, 1e-4, 0.3):
+            assert np.array_equal(S.points_out(P, eps2), OS.points_out(P, eps2))
+        assert np.array_equal(S.nearest(P)[2], OS.nearest(P)[2])
+        assert len(S.points_out(np.zeros((0, 3)), 1e-3)) == 0
+        assert np.array_equal(S.points_out(P[:1], 1e-4), OS.points_out(P[:1], 1e-4))
+    # degenerate facets (the reference's boundary mesh stores edges as degenerate triangles, Preprocess.cpp:192-197)
+    Fd = np.array([[0, 1, 1], [1, 2, 2], [2, 3, 3], [0, 1, 2]], dtype=np.uint32)
+    S, OS = tw.Surface(ctx, V, Fd), oracle.Surface(V, Fd)
+    assert np.array_equal(S.nearest(P)[2], OS.nearest(P)[2])
+    assert np.array_equal(S.points_out(P, 1e-2), OS.points_out(P, 1e-2))
+
+
+def test_sample_triangle_device_bit_exact(ctx, oracle):
+    rng = np.random.default_rng(4)
+    for it in range(60):
+        tri = rng.normal(size=(3, 3)) * rng.choice([0.0005, 0.003, 0.01, 0.05])
+        if it % 5 == 0:
+            tri = np.round(tri * 100) / 100
+        if it % 7 == 0:
+            tri = np.array([[0, 0, 0], [0.05, 0, 0], [0, 0.05, 0]]) + rng.integers(-3, 3, size=3)
+        sd = 1e-3 if it % 2 else 2.5e-3
+        assert np.array_equal(ctx.sample_triangle(tri, sd), oracle.sample_triangle(tri, sd))
+
+
+def test_faces_out_exact(knot, oracle):
+    V, F, S, OS = knot
+    for eps_rel, edge in ((2e-3, 0.02), (1e-3, 0.05), (4e-3, 0.004)):
+        sd, eps, eps2 = synth.state_eps(eps_rel)
+        T = synth.face_queries(V, F, 1500, edge, eps, seed=int(edge * 1e4))
+        T[::97] = np.array([0, 0, 5, 1, 1, 6, 2, 2, 7.0])      # collinear -> IN (LocalOperations.cpp:1048)
+        got = S.faces_out(T, sd, eps2)
+        ref, ns = OS.faces_out(T, sd, eps2, threads=4)
+        assert np.array_equal(got, ref)
+        assert 0.05 < got.mean() < 0.95
+    # faces of the surface itself are IN; pushed far away they are OUT
+    tri = V[F[:500].astype(np.int64)].reshape(-1, 9)
+    assert not S.faces_out(tri, sd, eps2).any()
+    assert S.faces_out(tri + 0.05, sd, eps2).all()
+
+
+def test_full_size_config2(ctx, oracle):
+    """BASELINE config 2 at full size (200 000 triangles, 10 M points): subsample vs the oracle + properties."""
+    V, F = synth.torus_knot(1000, 100)
+    assert len(F) == 200000
+    S = tw.Surface(ctx, V, F)
+    sd, eps, eps2 = synth.state_eps(1e-3)
+    n = 10_000_000
+    rng = np.random.default_rng(1)
+    # cheap full-size generator: facet barycentric samples with normal offsets (half of them exactly on facets)
+    tri = V[F.astype(np.int64)]
+    f = rng.integers(0, len(F), size=n)
+    w = rng.dirichlet([1, 1, 1], size=n)
+    P = (tri[f] * w[:, :, None]).sum(1)
+    nrm = np.cross(tri[f, 1] - tri[f, 0], tri[f, 2] - tri[f, 0])
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    off = rng.normal(0, eps, size=n)
+    off[: n // 2] = 0.0
+    P = P + nrm * off[:, None]
+    out = S.points_out(P, eps2)
+    # points within eps*(1-1e-6) of their own facet's plane offset are IN; idempotent; order independent
+    assert not out[np.abs(off) < eps * (1 - 1e-6)].any()
+    idx = rng.choice(n, 200000, replace=False)
+    OS = oracle.Surface(V, F)
+    assert np.array_equal(out[idx], OS.points_out(P[idx], eps2, threads=8))
+    perm = rng.permutation(n)[:2_000_000]
+    assert np.array_equal(S.points_out(P[perm], eps2), out[perm])

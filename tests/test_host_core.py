@@ -1,0 +1,88 @@
+"""CPU tier: the product's numeric core (tw_math.cuh / sampling.cuh, the source the kernels execute) compiled for the
+host (tests/host_harness.cpp) against the oracle. Bit exact for distances, samples and predicates; AMIPS closed form
+within 1e-9 of the tensor max-norm."""
+import ctypes as C
+
+import numpy as np
+
+from conftest import amips_close
+from tetwild_b200 import synth
+
+_dp = C.POINTER(C.c_double)
+
+
+def P(a):
+    return a.ctypes.data_as(_dp)
+
+
+def normwise(a, b):
+    a2, b2 = a.reshape(len(a), -1), b.reshape(len(b), -1)
+    return (np.abs(a2 - b2).max(1) / np.maximum(np.abs(b2).max(1), 1e-300)).max()
+
+
+def test_amips_closed_form(harness, oracle):
+    T = np.ascontiguousarray(synth.random_tets(20000, seed=7))
+    n = T.shape[1]
+    E, J, H = np.empty(n), np.empty((n, 3)), np.empty((n, 9))
+    harness.hh_amips_ejh_batch(P(T), C.c_uint64(n), P(E), P(J), P(H))
+    Eo, Jo, Ho = oracle.amips_ejh_soa(T, threads=4)
+    assert max(amips_close(T, (E, J, H), (Eo, Jo, Ho))) < 1e-9
+    if oracle.ref_available():
+        assert max(amips_close(T, (E, J, H), oracle.ref_amips_ejh_soa(T, threads=4))) < 1e-9
+
+
+def test_point_triangle_distance_bit_exact(harness, oracle):
+    rng = np.random.default_rng(3)
+    for it in range(20000):
+        v = rng.normal(size=(3, 3)) * rng.choice([1, 0.01])
+        p = rng.normal(size=3) * rng.choice([1, 0.02, 3])
+        if it % 7 == 0:
+            p = v[0] * 0.3 + v[1] * 0.3 + v[2] * 0.4
+        if it % 11 == 0:
+            v[2] = v[0] + (v[1] - v[0]) * rng.uniform()
+        if it % 13 == 0:
+            v[2] = v[1].copy()
+        near = np.empty(3)
+        d = harness.hh_tri_sqdist(P(p), P(v[0]), P(v[1]), P(v[2]), P(near))
+        d2, n2 = oracle.point_triangle_sqdist(p, v[0], v[1], v[2])
+        assert d == d2 and np.array_equal(near, n2)
+
+
+def test_sampling_bit_exact(harness, oracle):
+    rng = np.random.default_rng(4)
+    for it in range(400):
+        tri = rng.normal(size=(3, 3)) * rng.choice([0.003, 0.01, 0.05, 0.2])
+        if it % 5 == 0:
+            tri = np.round(tri * 100) / 100
+        if it % 17 == 0:
+            tri = np.array([[0, 0, 0], [0.05, 0, 0], [0, 0.05, 0]]) + rng.integers(-3, 3, size=3)
+        sd = 1e-3 if it % 2 else 2.5e-3
+        tri = np.ascontiguousarray(tri.reshape(9), dtype=np.float64)
+        ref = oracle.sample_triangle(tri, sd)
+        out = np.empty((len(ref) + 8, 3))
+        n = harness.hh_sample_triangle(P(tri), C.c_double(sd), P(out), C.c_uint64(len(out)))
+        assert n == len(ref) and np.array_equal(out[:n], ref)
+
+
+def test_predicates(harness, oracle):
+    rng = np.random.default_rng(2)
+    for it in range(3000):
+        a, b, c = rng.normal(size=(3, 3))
+        if it % 3 == 0:
+            w = rng.dirichlet([1, 1, 1])
+            d = w[0] * a + w[1] * b + w[2] * c
+        elif it % 3 == 1:
+            a, b, c = np.round(a * 8) / 8, np.round(b * 8) / 8, np.round(c * 8) / 8
+            w = np.round(rng.dirichlet([1, 1, 1]) * 4) / 4
+            w[2] = 1 - w[0] - w[1]
+            d = w[0] * a + w[1] * b + w[2] * c
+        else:
+            d = rng.normal(size=3)
+        a, b, c, d = [np.ascontiguousarray(x) for x in (a, b, c, d)]
+        s = oracle.orient3d_exact(a, b, c, d)
+        assert harness.hh_orient3d(P(a), P(b), P(c), P(d)) == s
+        assert harness.hh_orient3d_exact(P(a), P(b), P(c), P(d)) == s
+        assert harness.hh_cgal_orientation(P(d), P(a), P(b), P(c)) == s
+    z = [np.array(x, dtype=np.float64) for x in ([0, 0, 0], [1, 1, 1], [2, 2, 2], [2, 2, 2.0000000001])]
+    assert harness.hh_triangle_is_degenerate(P(z[0]), P(z[1]), P(z[2])) == 1
+    assert harness.hh_triangle_is_degenerate(P(z[0]), P(z[1]), P(z[3])) == 0

@@ -1,0 +1,193 @@
+"""CPU tier: the oracle restatement is pinned (a) to the committed golden vectors that were produced by the
+reference's own code (tests/golden/make_golden.py) and (b), when oracle/_ref is present, to the reference itself on
+larger seeded inputs. Tolerances: AMIPS 1e-9 relative to the tensor's max-norm; everything else bit exact."""
+import hashlib
+import math
+
+import numpy as np
+import pytest
+
+from conftest import amips_close, load_golden, unhex
+from tetwild_b200 import synth
+
+
+def normwise(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    a2, b2 = a.reshape(len(a), -1), b.reshape(len(b), -1)
+    return (np.abs(a2 - b2).max(1) / np.maximum(np.abs(b2).max(1), 1e-300)).max()
+
+
+def test_amips_golden(oracle):
+    g = load_golden("amips_golden.json")
+    n = g["n"]
+    T = unhex(g["T_rows_12xn"], (12, n))
+    E, J, H = oracle.amips_ejh_soa(T)
+    assert max(amips_close(T, (E, J, H), (unhex(g["E"]), unhex(g["J"], (n, 3)), unhex(g["H"], (n, 9))))) < 1e-9
+    # known answers of SURVEY.md 8c: regular tet E = 3 (README.md:141), corner tet
+    assert abs(unhex(g["E"])[0] - 3.0) < 1e-14
+    assert abs(unhex(g["E"])[1] - 3.571652366928451) < 1e-14
+    assert abs(E[0] - 3.0) < 1e-13 and np.abs(J[0]).max() < 1e-13
+
+
+def test_amips_invariants(oracle):
+    rng = np.random.default_rng(5)
+    T = synth.random_tets(200, seed=9, scale_lo=0.5, scale_hi=2.0, trans=1.0)
+    E = oracle.amips_energy_soa(T)
+    assert (E >= 3.0 - 1e-9).all()
+    # swapping two vertices leaves E unchanged: the MAX_ENERGY gate must come from the orientation predicate
+    T2 = T.copy()
+    T2[3:6], T2[6:9] = T[6:9].copy(), T[3:6].copy()
+    assert np.allclose(oracle.amips_energy_soa(T2), E, rtol=1e-12)
+    X = T.T.reshape(-1, 4, 3)
+    V = X.reshape(-1, 3)
+    tets = np.arange(len(V), dtype=np.int32).reshape(-1, 4)
+    q = oracle.amips_quality(V, tets)
+    assert np.allclose(q, E, rtol=1e-12)
+    tets_flipped = tets[:, [0, 2, 1, 3]]
+    assert (oracle.amips_quality(V, tets_flipped) == oracle.MAX_ENERGY).all()
+    # uniform scale / translation invariance, J ~ finite difference of E
+    E3 = oracle.amips_energy_soa(T * 3.0 + 0.25)
+    assert np.allclose(E3, E, rtol=1e-10)
+    t = T[:, 0].copy()
+    J = oracle.amips_jacobian(t)
+    Hm = oracle.amips_hessian(t)
+    h = 1e-6
+    for k in range(3):
+        tp, tm = t.copy(), t.copy()
+        tp[k] += h
+        tm[k] -= h
+        assert abs((oracle.amips_energy(tp) - oracle.amips_energy(tm)) / (2 * h) - J[k]) < 1e-6 * max(1, abs(J[k]))
+        fd = (oracle.amips_jacobian(tp) - oracle.amips_jacobian(tm)) / (2 * h)
+        assert np.abs(fd - Hm[k]).max() < 1e-5 * max(1, np.abs(Hm).max())
+
+
+def test_sample_golden(oracle):
+    g = load_golden("sample_golden.json")
+    for c in g["cases"]:
+        tri, sd = unhex(c["tri"], (3, 3)), float.fromhex(c["sd"])
+        ps = oracle.sample_triangle(tri, sd)
+        assert len(ps) == c["count"]
+        assert hashlib.sha256(np.ascontiguousarray(ps).tobytes()).hexdigest() == c["sha256"]
+
+
+def test_sample_edge_cases(oracle):
+    tiny = np.array([[0, 0, 0], [1e-4, 0, 0], [0, 1e-4, 0.0]])
+    assert len(oracle.sample_triangle(tiny, 1e-3)) == 3  # Common.cpp:154-158
+    assert oracle.triangle_is_degenerate([0, 0, 0], [1, 1, 1], [2, 2, 2])
+    assert not oracle.triangle_is_degenerate([0, 0, 0], [1, 1, 1], [2, 2, 2.0000000001])
+
+
+def test_tree_golden(oracle):
+    g = load_golden("tree_golden.json")
+    V, F = synth.torus_knot(60, 12)
+    S = oracle.Surface(V, F)
+    P = unhex(g["P"], (-1, 3))
+    eps2 = float.fromhex(g["eps2"])
+    f, q, d = S.nearest(P)
+    assert np.array_equal(d, unhex(g["nearest_d2"]))
+    assert np.array_equal(q, unhex(g["nearest_pt"], (-1, 3)))
+    assert np.array_equal(f, np.array(g["nearest_facet_original_ids"], dtype=np.uint32))
+    out = S.points_out(P, eps2)
+    assert np.array_equal(out, np.array(g["out"], dtype=np.uint8))
+    assert np.array_equal(S.points_out(P, eps2, brute=True), out)
+    assert 0.2 < out.mean() < 0.8
+
+
+def test_envelope_known_answers(oracle):
+    V, F = synth.icosphere(2)
+    S = oracle.Surface(V, F)
+    tri = V[F[:50].astype(np.int64)]
+    on = tri.mean(1)  # points exactly on facets -> IN for any eps
+    assert not S.points_out(on, 1e-12).any()
+    far = on * 3.0
+    assert S.points_out(far, 1e-6).all()
+    # faces of the surface itself are inside the envelope; the same faces pushed out by 10 eps are not
+    sd, eps, eps2 = synth.state_eps(1e-2)
+    out, ns = S.faces_out(tri.reshape(-1, 9), sd, eps2)
+    assert not out.any() and (ns >= 3).all()
+    out2, _ = S.faces_out((tri * 1.2).reshape(-1, 9), sd, eps2)
+    assert out2.all()
+    deg = np.array([[0, 0, 5, 1, 1, 6, 2, 2, 7.0]])
+    assert not S.faces_out(deg, sd, eps2)[0].any()  # degenerate triangle -> IN (LocalOperations.cpp:1048)
+
+
+def test_winding_known_answers(oracle):
+    V, F = synth.uv_sphere(24, 24, noise=0.0)
+    r = np.linalg.norm(V, axis=1).max()
+    Q = np.array([[0, 0, 0], [0.3 * r, 0.1 * r, -0.2 * r], [2 * r, 0, 0], [0, -3 * r, r]])
+    W = oracle.winding_direct(V, F, Q)
+    assert np.allclose(W, [1, 1, 0, 0], atol=1e-12)
+    assert np.allclose(oracle.winding_direct(V, F[:, [0, 2, 1]], Q), [-1, -1, 0, 0], atol=1e-12)
+    assert np.allclose(oracle.winding_direct(V, np.concatenate([F, F]), Q), [2, 2, 0, 0], atol=1e-12)
+    keep, W2, retried = oracle.inout_filter(V, F[:, [0, 2, 1]], Q)
+    assert retried and list(keep) == [1, 1, 0, 0]
+    V2, F2 = synth.uv_sphere(60, 60)
+    Q2 = synth.winding_queries(V2, 3000)
+    T = oracle.WindingTree(V2, F2)
+    assert np.abs(T.eval(Q2) - oracle.winding_direct(V2, F2, Q2, threads=4)).max() < 1e-11
+
+
+def test_predicates_exact(oracle):
+    from fractions import Fraction
+    rng = np.random.default_rng(1)
+
+    def sign(a, b, c, d):
+        A = [[Fraction(float(x)) for x in p] for p in (a, b, c, d)]
+        r = [[A[i][k] - A[3][k] for k in range(3)] for i in range(3)]
+        det = (r[0][0] * (r[1][1] * r[2][2] - r[1][2] * r[2][1]) - r[0][1] * (r[1][0] * r[2][2] - r[1][2] * r[2][0])
+               + r[0][2] * (r[1][0] * r[2][1] - r[1][1] * r[2][0]))
+        return (det > 0) - (det < 0)
+
+    for it in range(600):
+        a, b, c = rng.normal(size=(3, 3))
+        if it % 3 == 0:
+            w = rng.dirichlet([1, 1, 1])
+            d = w[0] * a + w[1] * b + w[2] * c
+        elif it % 3 == 1:
+            a, b, c = np.round(a * 8) / 8, np.round(b * 8) / 8, np.round(c * 8) / 8
+            w = np.round(rng.dirichlet([1, 1, 1]) * 4) / 4
+            w[2] = 1 - w[0] - w[1]
+            d = w[0] * a + w[1] * b + w[2] * c
+        else:
+            d = rng.normal(size=3)
+        assert oracle.orient3d_exact(a, b, c, d) == sign(a, b, c, d)
+        assert oracle.cgal_orientation(d, a, b, c) == sign(a, b, c, d)
+
+
+# ---------------------------------------------------------------------------------- against the reference itself
+def _need_ref(oracle):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref not present (needs /root/reference at build time); golden vectors cover this box")
+
+
+def test_amips_vs_reference(oracle):
+    _need_ref(oracle)
+    T = synth.random_tets(50000, seed=7)
+    Eo, Jo, Ho = oracle.amips_ejh_soa(T, threads=4)
+    Er, Jr, Hr = oracle.ref_amips_ejh_soa(T, threads=4)
+    assert max(amips_close(T, (Eo, Jo, Ho), (Er, Jr, Hr))) < 1e-9
+
+
+def test_sampling_vs_reference(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(11)
+    for it in range(300):
+        tri = rng.normal(size=(3, 3)) * rng.choice([0.003, 0.01, 0.05])
+        if it % 5 == 0:
+            tri = np.round(tri * 100) / 100
+        sd = 1e-3 if it % 2 else 2.5e-3
+        assert np.array_equal(oracle.sample_triangle(tri, sd), oracle.ref_sample_triangle(tri, sd))
+
+
+def test_tree_vs_reference(oracle):
+    _need_ref(oracle)
+    V, F = synth.torus_knot(120, 24)
+    S = oracle.Surface(V, F)
+    order = S.order()
+    RT = oracle.RefTree(V, F[order])
+    sd, eps, eps2 = synth.state_eps(2e-3)
+    P = synth.envelope_points(V, F, 20000, eps)
+    f1, q1, d1 = S.nearest(P, threads=4)
+    f2, q2, d2 = RT.nearest(P, threads=4)
+    assert np.array_equal(d1, d2) and np.array_equal(q1, q2) and np.array_equal(f1, order[f2])
+    assert np.array_equal(S.points_out(P, eps2, threads=4), RT.points_out(P, eps2, threads=4)[0])

@@ -1,0 +1,308 @@
+"""ctypes binding of include/tetwild_gpu.h.
+
+Host-buffer methods take/return numpy arrays (copies are part of the call, like the C ABI); methods ending in `_dev`
+take raw device pointers (ints, e.g. torch.Tensor.data_ptr()) and a CUDA stream handle and are asynchronous.
+Names follow the reference: Surface ~ GEO::MeshFacetsAABBWithEps, Context.amips_* ~ LocalOperations /
+VertexSmoother members, Winding ~ igl::winding_number.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_ENERGY = 1e50
+NO_FACET = 0xFFFFFFFF
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libtetwild_gpu.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+
+
+class TetWildGPUError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """Load libtetwild_gpu.so. Fails loudly when the CUDA extension has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise TetWildGPUError(
+            "libtetwild_gpu.so is missing at %s: build it with `python -m tetwild_b200.build` "
+            "(there is no CPU fallback)" % _LIB_PATH)
+    L = C.CDLL(_LIB_PATH)
+    L.twg_last_error.restype = C.c_char_p
+    L.twg_version.restype = C.c_char_p
+    L.twg_launch_count.restype = C.c_uint64
+    L.twg_surface_num_facets.restype = C.c_uint32
+    L.twg_last_error.argtypes = [_vp]
+    L.twg_launch_count.argtypes = [_vp]
+    L.twg_destroy.argtypes = [_vp]
+    L.twg_surface_destroy.argtypes = [_vp]
+    L.twg_winding_destroy.argtypes = [_vp]
+    L.twg_destroy.restype = None
+    L.twg_surface_destroy.restype = None
+    L.twg_winding_destroy.restype = None
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+def _dev(p):
+    return C.c_void_p(int(p) if p else 0)
+
+
+class Context:
+    """twg_ctx: one device."""
+
+    def __init__(self, device=0):
+        self._L = load_library()
+        h = C.c_void_p()
+        rc = self._L.twg_create(C.byref(h), C.c_int(device))
+        if rc != 0:
+            raise TetWildGPUError("twg_create(device=%d) failed with code %d (no sm_100-class GPU? there is no CPU fallback)" % (device, rc))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.twg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise TetWildGPUError("libtetwild_gpu error %d: %s" % (rc, self._L.twg_last_error(self.h).decode()))
+
+    @property
+    def launches(self):
+        return int(self._L.twg_launch_count(self.h))
+
+    def synchronize(self):
+        self._check(self._L.twg_synchronize(self.h))
+
+    # ---- AMIPS ----
+    @staticmethod
+    def _soa_ptrs(T):
+        T = _f64(T)
+        assert T.ndim == 2 and T.shape[0] == 12, "T must be (12, n): row 3*i+k = coordinate k of vertex i"
+        return T, (C.c_void_p * 12)(*[T[k].ctypes.data for k in range(12)])
+
+    def amips_energy_soa(self, T):
+        """energy_ispc(V1_x..V4_z, E, count) (src/ispc/energy.ispc:7-21)"""
+        T, ptrs = self._soa_ptrs(T)
+        n = T.shape[1]
+        E = np.empty(n)
+        self._check(self._L.twg_amips_energy_soa(self.h, ptrs, _ptr(E), C.c_uint64(n)))
+        return E
+
+    def amips_ejh_soa(self, T, want=(True, True, True)):
+        T, ptrs = self._soa_ptrs(T)
+        n = T.shape[1]
+        E = np.empty(n) if want[0] else None
+        J = np.empty((n, 3)) if want[1] else None
+        H = np.empty((n, 9)) if want[2] else None
+        self._check(self._L.twg_amips_ejh_soa(self.h, ptrs, _ptr(E), _ptr(J), _ptr(H), C.c_uint64(n)))
+        return E, J, H
+
+    def amips_ejh_soa_dev(self, dT12, dE, dJ3, dH9, n, stream=0):
+        ptrs = (C.c_void_p * 12)(*[int(p) for p in dT12])
+        self._check(self._L.twg_amips_ejh_soa_dev(self.h, ptrs, _dev(dE), _dev(dJ3), _dev(dH9), C.c_uint64(n), _dev(stream)))
+
+    def amips_energy_soa_dev(self, dT12, dE, n, stream=0):
+        ptrs = (C.c_void_p * 12)(*[int(p) for p in dT12])
+        self._check(self._L.twg_amips_energy_soa_dev(self.h, ptrs, _dev(dE), C.c_uint64(n), _dev(stream)))
+
+    def amips_quality(self, V, tets):
+        """calTetQualities (LocalOperations.cpp:695-773): slim_energy per tet"""
+        V = _f64(V)
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        out = np.empty(len(tets))
+        self._check(self._L.twg_amips_quality(self.h, _ptr(V), C.c_uint32(len(V)), _ptr(tets), C.c_uint64(len(tets)), _ptr(out)))
+        return out
+
+    def amips_quality_dev(self, dV, nV, dTets, nT, dSlim, stream=0):
+        self._check(self._L.twg_amips_quality_dev(self.h, _dev(dV), C.c_uint32(nV), _dev(dTets), C.c_uint64(nT), _dev(dSlim), _dev(stream)))
+
+    def amips_ring_ejh(self, V, tets, group_off, center, t_ids=None):
+        """VertexSmoother::NewtonsUpdate for many one-rings (VertexSmoother.cpp:627-702)"""
+        V = _f64(V)
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        off = np.ascontiguousarray(group_off, dtype=np.uint64)
+        center = np.ascontiguousarray(center, dtype=np.int32)
+        tid = np.ascontiguousarray(t_ids, dtype=np.int32) if t_ids is not None else None
+        g = len(center)
+        E, J, H, ok = np.empty(g), np.empty((g, 3)), np.empty((g, 9)), np.empty(g, dtype=np.uint8)
+        self._check(self._L.twg_amips_ring_ejh(self.h, _ptr(V), C.c_uint32(len(V)), _ptr(tets), C.c_uint64(len(tets)), _ptr(tid),
+                                               _ptr(off), _ptr(center), C.c_uint64(g), _ptr(E), _ptr(J), _ptr(H), _ptr(ok)))
+        return E, J, H, ok
+
+    def amips_ring_ejh_dev(self, dV, nV, dTets, nT, dTids, dOff, dCenter, nG, dE, dJ3, dH9, dOk, stream=0):
+        self._check(self._L.twg_amips_ring_ejh_dev(self.h, _dev(dV), C.c_uint32(nV), _dev(dTets), C.c_uint64(nT), _dev(dTids), _dev(dOff),
+                                                   _dev(dCenter), C.c_uint64(nG), _dev(dE), _dev(dJ3), _dev(dH9), _dev(dOk), _dev(stream)))
+
+    def amips_ring_energy(self, V, tets, group_off, t_ids=None):
+        """VertexSmoother::getNewEnergy for many one-rings (VertexSmoother.cpp:544-625)"""
+        V = _f64(V)
+        tets = np.ascontiguousarray(tets, dtype=np.int32)
+        off = np.ascontiguousarray(group_off, dtype=np.uint64)
+        tid = np.ascontiguousarray(t_ids, dtype=np.int32) if t_ids is not None else None
+        g = len(off) - 1
+        E = np.empty(g)
+        self._check(self._L.twg_amips_ring_energy(self.h, _ptr(V), C.c_uint32(len(V)), _ptr(tets), C.c_uint64(len(tets)), _ptr(tid),
+                                                  _ptr(off), C.c_uint64(g), _ptr(E)))
+        return E
+
+    # ---- sampling (debug / parity) ----
+    def sample_triangle(self, tri, sampling_dist):
+        t = _f64(tri).reshape(9)
+        cnt = C.c_uint64(0)
+        self._check(self._L.twg_sample_triangle(self.h, _ptr(t), C.c_double(sampling_dist), C.c_void_p(0), C.c_uint64(0), C.byref(cnt)))
+        out = np.empty((cnt.value, 3))
+        if cnt.value:
+            self._check(self._L.twg_sample_triangle(self.h, _ptr(t), C.c_double(sampling_dist), _ptr(out), C.c_uint64(cnt.value), C.byref(cnt)))
+        return out
+
+    # ---- winding one-shots ----
+    def winding_number(self, V, F, Q, want_w=True, want_keep=True):
+        """igl::winding_number(V,F,O,W) (InoutFiltering.cpp:45)"""
+        V, Q = _f64(V), _f64(Q)
+        F = np.ascontiguousarray(F, dtype=np.uint32)
+        W = np.empty(len(Q)) if want_w else None
+        keep = np.empty(len(Q), dtype=np.uint8) if want_keep else None
+        self._check(self._L.twg_winding_number(self.h, _ptr(V), C.c_uint32(len(V)), _ptr(F), C.c_uint32(len(F)), _ptr(Q),
+                                               C.c_uint64(len(Q)), _ptr(W), _ptr(keep)))
+        return W, keep
+
+    def inout_filter(self, V, F, Q):
+        """InoutFiltering::filter decision incl. flip-and-retry (InoutFiltering.cpp:45-75) -> (keep, retried)"""
+        V, Q = _f64(V), _f64(Q)
+        F = np.ascontiguousarray(F, dtype=np.uint32)
+        keep = np.empty(len(Q), dtype=np.uint8)
+        r = C.c_int(0)
+        self._check(self._L.twg_inout_filter(self.h, _ptr(V), C.c_uint32(len(V)), _ptr(F), C.c_uint32(len(F)), _ptr(Q),
+                                             C.c_uint64(len(Q)), _ptr(keep), C.byref(r)))
+        return keep, bool(r.value)
+
+
+class Surface:
+    """twg_surface ~ GEO::MeshFacetsAABBWithEps (src/tetwild/geogram/mesh_AABB.h:64-421), built on the device."""
+
+    def __init__(self, ctx, V, F):
+        self.ctx = ctx
+        self._L = ctx._L
+        V = _f64(V)
+        F = np.ascontiguousarray(F, dtype=np.uint32)
+        h = C.c_void_p()
+        ctx._check(self._L.twg_surface_create(ctx.h, _ptr(V), C.c_uint32(len(V)), _ptr(F), C.c_uint32(len(F)), C.byref(h)))
+        self.h = h
+        self.num_facets = len(F)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.twg_surface_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def points_out(self, P, eps2):
+        """out[i] = isPointOutEnvelop(P[i]) (LocalOperations.cpp:1034-1044)"""
+        P = _f64(P)
+        out = np.empty(len(P), dtype=np.uint8)
+        self.ctx._check(self._L.twg_envelope_points_out(self.h, _ptr(P), C.c_uint64(len(P)), C.c_double(eps2), _ptr(out)))
+        return out
+
+    def points_out_dev(self, dP, n, eps2, dOut, stream=0):
+        self.ctx._check(self._L.twg_envelope_points_out_dev(self.h, _dev(dP), C.c_uint64(n), C.c_double(eps2), _dev(dOut), _dev(stream)))
+
+    def faces_out(self, tris, sampling_dist, eps2):
+        """out[i] = isFaceOutEnvelop(tris[i]) (LocalOperations.cpp:967-976, :1046-1109)"""
+        T = _f64(tris).reshape(-1, 9)
+        out = np.empty(len(T), dtype=np.uint8)
+        self.ctx._check(self._L.twg_envelope_faces_out(self.h, _ptr(T), C.c_uint64(len(T)), C.c_double(sampling_dist), C.c_double(eps2), _ptr(out)))
+        return out
+
+    def faces_out_dev(self, dTris, n, sampling_dist, eps2, dOut, stream=0):
+        self.ctx._check(self._L.twg_envelope_faces_out_dev(self.h, _dev(dTris), C.c_uint64(n), C.c_double(sampling_dist), C.c_double(eps2),
+                                                           _dev(dOut), _dev(stream)))
+
+    def nearest(self, P):
+        """nearest_facet (mesh_AABB.h:130-141) -> (facet ids in the caller's numbering, nearest points, d2)"""
+        P = _f64(P)
+        n = len(P)
+        f, q, d = np.empty(n, dtype=np.uint32), np.empty((n, 3)), np.empty(n)
+        self.ctx._check(self._L.twg_nearest(self.h, _ptr(P), C.c_uint64(n), _ptr(f), _ptr(q), _ptr(d)))
+        return f, q, d
+
+    def nearest_dev(self, dP, n, dFacet, dNearest, dD2, stream=0):
+        self.ctx._check(self._L.twg_nearest_dev(self.h, _dev(dP), C.c_uint64(n), _dev(dFacet), _dev(dNearest), _dev(dD2), _dev(stream)))
+
+    def squared_distance(self, P):
+        """squared_distance (mesh_AABB.h:221-226)"""
+        P = _f64(P)
+        d = np.empty(len(P))
+        self.ctx._check(self._L.twg_nearest(self.h, _ptr(P), C.c_uint64(len(P)), C.c_void_p(0), C.c_void_p(0), _ptr(d)))
+        return d
+
+
+class Winding:
+    """twg_winding: winding-number hierarchy over a surface (igl::winding_number, InoutFiltering.cpp:45)."""
+
+    def __init__(self, ctx, V, F):
+        self.ctx = ctx
+        self._L = ctx._L
+        V = _f64(V)
+        F = np.ascontiguousarray(F, dtype=np.uint32)
+        h = C.c_void_p()
+        ctx._check(self._L.twg_winding_create(ctx.h, _ptr(V), C.c_uint32(len(V)), _ptr(F), C.c_uint32(len(F)), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.twg_winding_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def eval(self, Q, want_w=True, want_keep=True):
+        Q = _f64(Q)
+        W = np.empty(len(Q)) if want_w else None
+        keep = np.empty(len(Q), dtype=np.uint8) if want_keep else None
+        self.ctx._check(self._L.twg_winding_eval(self.h, _ptr(Q), C.c_uint64(len(Q)), _ptr(W), _ptr(keep)))
+        return W, keep
+
+    def eval_dev(self, dQ, n, dW, dKeep, stream=0):
+        self.ctx._check(self._L.twg_winding_eval_dev(self.h, _dev(dQ), C.c_uint64(n), _dev(dW), _dev(dKeep), _dev(stream)))
+
+    def stats(self):
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._L.twg_winding_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return {"nodes": a.value, "cap_segments": b.value, "triangles": c.value}

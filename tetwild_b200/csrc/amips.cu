@@ -1,0 +1,400 @@
+// amips.cu -- batched conformal-AMIPS kernels (FP64) and their C ABI.
+//
+// Replaces, for batches: energy_ispc (src/ispc/energy.ispc:7-65), comformalAMIPS{Energy,Jacobian,Hessian}_new
+// (src/tetwild/LocalOperations.cpp:28-291), calTetQualities (:695-773, :862-884), VertexSmoother::NewtonsUpdate
+// (src/tetwild/VertexSmoother.cpp:627-702) and getNewEnergy (:544-625). Math: tw_math.cuh::amips_eval.
+//
+// Kernels
+//   amips_soa_kernel     flat SoA, one thread per VEC tets, 128-bit streaming loads of the 12 coordinate arrays,
+//                        E written coalesced, J3/H9 (AoS per tet, as the reference lays them out) transposed
+//                        through shared memory so that global stores are full 128-bit coalesced.
+//                        HBM-bound: 96 B in + 8/32/104 B out per tet.
+//   amips_quality_kernel indexed gather (int4 tet load + 4 vertex gathers), exact orientation gate.
+//   amips_ring_kernel    one warp per one-ring group, lanes over member tets, coalesced index loads, shuffle
+//                        reduction of the 13 outputs, lane 0 stores. FP64-pipe-bound.
+#include "common.cuh"
+
+namespace {
+
+constexpr int AM_THREADS = 128;
+
+struct SoaArgs {
+    const double* T[12];
+    double* E;
+    double* J3;
+    double* H9;
+    uint64_t n;
+};
+
+template <int VEC, bool JH>
+__global__ void __launch_bounds__(AM_THREADS) amips_soa_kernel(SoaArgs a) {
+    constexpr int TILE = AM_THREADS * VEC;
+    extern __shared__ __align__(16) double sm[];  // JH: [TILE*3] J then [TILE*9] H
+    double* sJ = sm;
+    double* sH = sm + TILE * 3;
+    const uint64_t n = a.n;
+    for (uint64_t base = (uint64_t)blockIdx.x * TILE; base < n; base += (uint64_t)gridDim.x * TILE) {
+        const uint64_t i0 = base + (uint64_t)threadIdx.x * VEC;
+        double x[VEC][12];
+        if (i0 + VEC <= n) {
+            if (VEC == 2) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    double2 v = ld_stream2(a.T[k] + i0);
+                    x[0][k] = v.x;
+                    x[VEC - 1][k] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) x[0][k] = __ldg(a.T[k] + i0);
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v)
+#pragma unroll
+                for (int k = 0; k < 12; ++k) x[v][k] = (i0 + v < n) ? __ldg(a.T[k] + i0 + v) : (double)((k * 7 + k / 3) % 5);
+        }
+        tw::Amips r[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) tw::amips_eval<JH>(x[v], r[v]);
+        if (a.E) {
+            if (VEC == 2 && i0 + VEC <= n) st_stream2(a.E + i0, make_double2(r[0].E, r[VEC - 1].E));
+            else {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v)
+                    if (i0 + v < n) a.E[i0 + v] = r[v].E;
+            }
+        }
+        if (JH) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                const int tl = threadIdx.x * VEC + v;
+                sJ[tl * 3 + 0] = r[v].J[0]; sJ[tl * 3 + 1] = r[v].J[1]; sJ[tl * 3 + 2] = r[v].J[2];
+                double* h = sH + tl * 9;
+                h[0] = r[v].H[0]; h[1] = r[v].H[1]; h[2] = r[v].H[2];
+                h[3] = r[v].H[1]; h[4] = r[v].H[3]; h[5] = r[v].H[4];
+                h[6] = r[v].H[2]; h[7] = r[v].H[4]; h[8] = r[v].H[5];
+            }
+            __syncthreads();
+            const uint64_t cnt = (n - base < (uint64_t)TILE) ? (n - base) : (uint64_t)TILE;
+            if (a.J3) {
+                double* dst = a.J3 + base * 3;
+                const int tot = (int)cnt * 3;
+                if (VEC == 2) {  // launcher guarantees 16-byte aligned outputs; TILE*3 is even
+                    for (int k = threadIdx.x * 2; k + 1 < tot; k += AM_THREADS * 2) st_stream2(dst + k, make_double2(sJ[k], sJ[k + 1]));
+                    if ((tot & 1) && threadIdx.x == 0) dst[tot - 1] = sJ[tot - 1];
+                } else {
+                    for (int k = threadIdx.x; k < tot; k += AM_THREADS) dst[k] = sJ[k];
+                }
+            }
+            if (a.H9) {
+                double* dst = a.H9 + base * 9;
+                const int tot = (int)cnt * 9;
+                if (VEC == 2) {
+                    for (int k = threadIdx.x * 2; k + 1 < tot; k += AM_THREADS * 2) st_stream2(dst + k, make_double2(sH[k], sH[k + 1]));
+                    if ((tot & 1) && threadIdx.x == 0) dst[tot - 1] = sH[tot - 1];
+                } else {
+                    for (int k = threadIdx.x; k < tot; k += AM_THREADS) dst[k] = sH[k];
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ void gather_vertex(const double* __restrict__ V, int32_t v, double* dst) {
+    const double* p = V + 3 * (size_t)v;
+    dst[0] = __ldg(p); dst[1] = __ldg(p + 1); dst[2] = __ldg(p + 2);
+}
+
+// calTetQuality_AMIPS (LocalOperations.cpp:862-884)
+__global__ void __launch_bounds__(256) amips_quality_kernel(const double* __restrict__ V, const int4* __restrict__ tets, uint64_t nT,
+                                                            double* __restrict__ slim) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nT; i += (uint64_t)gridDim.x * blockDim.x) {
+        const int4 t = __ldg(tets + i);
+        double x[12];
+        gather_vertex(V, t.x, x); gather_vertex(V, t.y, x + 3); gather_vertex(V, t.z, x + 6); gather_vertex(V, t.w, x + 9);
+        double e;
+        if (tw::exact::cgal_orientation(x, x + 3, x + 6, x + 9) != 1) {
+            e = TWG_MAX_ENERGY;
+        } else {
+            tw::Amips r;
+            tw::amips_eval<false>(x, r);
+            e = r.E;
+        }
+        if (isinf(e) || isnan(e) || e <= 0.0) e = TWG_MAX_ENERGY;
+        slim[i] = e;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// NewtonsUpdate (VertexSmoother.cpp:627-702): one warp per one-ring
+template <bool ENERGY_ONLY>
+__global__ void __launch_bounds__(256) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
+                                                         const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
+                                                         const int32_t* __restrict__ center, uint64_t nG, double* __restrict__ E,
+                                                         double* __restrict__ J3, double* __restrict__ H9, uint8_t* __restrict__ ok) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t g = warp; g < nG; g += nwarps) {
+        const uint64_t b = __ldg(off + g), e = __ldg(off + g + 1);
+        const int32_t c = ENERGY_ONLY ? 0 : __ldg(center + g);
+        double acc[13];
+#pragma unroll
+        for (int k = 0; k < 13; ++k) acc[k] = 0.0;
+        for (uint64_t k = b + lane; k < e; k += 32) {
+            const uint64_t ti = t_ids ? (uint64_t)__ldg(t_ids + k) : k;
+            const int4 t = __ldg(tets + ti);
+            int32_t v[4] = {t.x, t.y, t.z, t.w};
+            int start = 0;
+            if (!ENERGY_ONLY) {  // :640-646, first slot holding the center vertex
+                if (v[0] == c) start = 0;
+                else if (v[1] == c) start = 1;
+                else if (v[2] == c) start = 2;
+                else if (v[3] == c) start = 3;
+            }
+            double x[12];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int32_t vj = (start == 0) ? v[j] : (start == 1) ? v[(j + 1) & 3] : (start == 2) ? v[(j + 2) & 3] : v[(j + 3) & 3];
+                gather_vertex(V, vj, x + 3 * j);
+            }
+            tw::Amips r;
+            tw::amips_eval<!ENERGY_ONLY>(x, r);
+            acc[0] += r.E;
+            if (!ENERGY_ONLY) {
+                acc[1] += r.J[0]; acc[2] += r.J[1]; acc[3] += r.J[2];
+                acc[4] += r.H[0]; acc[5] += r.H[1]; acc[6] += r.H[2];
+                acc[7] += r.H[1]; acc[8] += r.H[3]; acc[9] += r.H[4];
+                acc[10] += r.H[2]; acc[11] += r.H[4]; acc[12] += r.H[5];
+            }
+        }
+        acc[0] = warp_sum(acc[0]);
+        if (!ENERGY_ONLY) {
+#pragma unroll
+            for (int k = 1; k < 13; ++k) acc[k] = warp_sum(acc[k]);
+        }
+        if (lane == 0) {
+            double en = acc[0];
+            if (ENERGY_ONLY) {  // getNewEnergy :619-622
+                if (isinf(en) || isnan(en) || en <= 0.0 || en > TWG_MAX_ENERGY) en = TWG_MAX_ENERGY;
+                E[g] = en;
+            } else {  // :680-699
+                bool good = true;
+                if (isinf(en)) en = TWG_MAX_ENERGY;
+                if (isnan(en)) good = false;
+                if (en <= 0.0) good = false;
+#pragma unroll
+                for (int k = 1; k < 13; ++k)
+                    if (!isfinite(acc[k])) good = false;
+                E[g] = en;
+                J3[g * 3 + 0] = acc[1]; J3[g * 3 + 1] = acc[2]; J3[g * 3 + 2] = acc[3];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) H9[g * 9 + k] = acc[4 + k];
+                if (ok) ok[g] = good ? 1 : 0;
+            }
+        }
+    }
+}
+
+inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
+
+int launch_soa(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, double* dH9, uint64_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    SoaArgs a;
+    bool vec = (n % 2 == 0) || true;
+    for (int k = 0; k < 12; ++k) { a.T[k] = dT[k]; vec = vec && aligned16(dT[k]); }
+    a.E = dE; a.J3 = dJ3; a.H9 = dH9; a.n = n;
+    vec = vec && (!dE || aligned16(dE)) && (!dJ3 || aligned16(dJ3)) && (!dH9 || aligned16(dH9));
+    const bool jh = (dJ3 != nullptr) || (dH9 != nullptr);
+    const int tile = AM_THREADS * (vec ? 2 : 1);
+    uint64_t blocks = (n + tile - 1) / tile;
+    const uint64_t maxb = (uint64_t)c->sm_count * 16;
+    if (blocks > maxb) blocks = maxb;
+    const size_t smem = jh ? (size_t)tile * 12 * sizeof(double) : 0;
+    if (vec) {
+        if (jh) TWG_LAUNCH(c, (amips_soa_kernel<2, true>), (unsigned)blocks, AM_THREADS, smem, st, a);
+        else TWG_LAUNCH(c, (amips_soa_kernel<2, false>), (unsigned)blocks, AM_THREADS, smem, st, a);
+    } else {
+        if (jh) TWG_LAUNCH(c, (amips_soa_kernel<1, true>), (unsigned)blocks, AM_THREADS, smem, st, a);
+        else TWG_LAUNCH(c, (amips_soa_kernel<1, false>), (unsigned)blocks, AM_THREADS, smem, st, a);
+    }
+    return 0;
+}
+
+cudaStream_t pick(twg_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->streams[0]; }
+
+unsigned grid_for(twg_ctx* c, uint64_t items, int per_block, int waves) {
+    uint64_t b = (items + per_block - 1) / per_block;
+    uint64_t m = (uint64_t)c->sm_count * waves;
+    if (b > m) b = m;
+    if (b == 0) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace
+
+extern "C" {
+
+int twg_amips_energy_soa_dev(twg_ctx* c, const double* const dT[12], double* dE, uint64_t n, void* stream) {
+    TWG_CHECK(c, c && dT && dE, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    return launch_soa(c, dT, dE, nullptr, nullptr, n, pick(c, stream));
+}
+
+int twg_amips_ejh_soa_dev(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, double* dH9, uint64_t n, void* stream) {
+    TWG_CHECK(c, c && dT, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    return launch_soa(c, dT, dE, dJ3, dH9, n, pick(c, stream));
+}
+
+int twg_amips_quality_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, double* dSlim, void* stream) {
+    (void)nV;
+    TWG_CHECK(c, c && dV && dTets && dSlim, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
+    if (nT == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, amips_quality_kernel, grid_for(c, nT, 256, 8), 256, 0, pick(c, stream), dV, (const int4*)dTets, nT, dSlim);
+    return 0;
+}
+
+int twg_amips_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dTids,
+                           const uint64_t* dOff, const int32_t* dCenter, uint64_t nG, double* dE, double* dJ3, double* dH9,
+                           uint8_t* dOk, void* stream) {
+    (void)nV; (void)nT;
+    TWG_CHECK(c, c && dV && dTets && dOff && dCenter && dE && dJ3 && dH9, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
+    if (nG == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
+               dCenter, nG, dE, dJ3, dH9, dOk);
+    return 0;
+}
+
+int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dTids,
+                              const uint64_t* dOff, uint64_t nG, double* dE, void* stream) {
+    (void)nV; (void)nT;
+    TWG_CHECK(c, c && dV && dTets && dOff && dE, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
+    if (nG == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
+               (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr);
+    return 0;
+}
+
+// ---- host-buffer entry points: chunked H2D -> kernel -> D2H pipeline over TWG_NUM_STREAMS streams ----
+int twg_amips_ejh_soa(twg_ctx* c, const double* const T[12], double* E, double* J3, double* H9, uint64_t n) {
+    TWG_CHECK(c, c && T, TWG_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t chunk = 1ull << 21;  // 2 Mi tets: 192 MiB in, up to 208 MiB out per slot
+    const int nout = (E ? 1 : 0) + (J3 ? 3 : 0) + (H9 ? 9 : 0);
+    const size_t per = (size_t)(12 + nout) * sizeof(double);
+    const uint64_t cmax = n < chunk ? ((n + 1) & ~1ull) : chunk;
+    for (int s = 0; s < TWG_NUM_STREAMS; ++s) TWG_TRY(twg_ensure_scratch(c, s, per * cmax));
+    int slot = 0;
+    for (uint64_t b = 0; b < n; b += chunk, slot = (slot + 1) % TWG_NUM_STREAMS) {
+        const uint64_t m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t st = c->streams[slot];
+        double* base = (double*)c->dscratch[slot];
+        const double* dT[12];
+        for (int k = 0; k < 12; ++k) {
+            dT[k] = base + (size_t)k * cmax;
+            TWG_CUDA(c, cudaMemcpyAsync((void*)dT[k], T[k] + b, m * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
+        double* dE = E ? base + (size_t)12 * cmax : nullptr;
+        double* dJ = J3 ? base + (size_t)(12 + (E ? 1 : 0)) * cmax : nullptr;
+        double* dH = H9 ? base + (size_t)(12 + (E ? 1 : 0) + (J3 ? 3 : 0)) * cmax : nullptr;
+        TWG_TRY(launch_soa(c, dT, dE, dJ, dH, m, st));
+        if (E) TWG_CUDA(c, cudaMemcpyAsync(E + b, dE, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (J3) TWG_CUDA(c, cudaMemcpyAsync(J3 + b * 3, dJ, m * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (H9) TWG_CUDA(c, cudaMemcpyAsync(H9 + b * 9, dH, m * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < TWG_NUM_STREAMS; ++s) TWG_CUDA(c, cudaStreamSynchronize(c->streams[s]));
+    return 0;
+}
+
+int twg_amips_energy_soa(twg_ctx* c, const double* const T[12], double* E, uint64_t n) {
+    TWG_CHECK(c, c && T && E, TWG_ERR_INVALID_ARG, "null argument");
+    return twg_amips_ejh_soa(c, T, E, nullptr, nullptr, n);
+}
+
+int twg_amips_quality(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, double* slim) {
+    TWG_CHECK(c, c && V && tets && slim, TWG_ERR_INVALID_ARG, "null argument");
+    if (nT == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    const size_t vb = ((size_t)nV * 3 * sizeof(double) + 255) & ~(size_t)255;
+    const size_t tb = ((size_t)nT * 16 + 255) & ~(size_t)255;
+    TWG_TRY(twg_ensure_scratch(c, 0, vb + tb + nT * sizeof(double)));
+    char* base = (char*)c->dscratch[0];
+    cudaStream_t st = c->streams[0];
+    TWG_CUDA(c, cudaMemcpyAsync(base, V, (size_t)nV * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TWG_CUDA(c, cudaMemcpyAsync(base + vb, tets, (size_t)nT * 16, cudaMemcpyHostToDevice, st));
+    TWG_TRY(twg_amips_quality_dev(c, (const double*)base, nV, (const int32_t*)(base + vb), nT, (double*)(base + vb + tb), st));
+    TWG_CUDA(c, cudaMemcpyAsync(slim, base + vb + tb, nT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TWG_CUDA(c, cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int ring_host(twg_ctx* c, bool energy_only, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, const int32_t* t_ids,
+                     const uint64_t* off, const int32_t* center, uint64_t nG, double* E, double* J3, double* H9, uint8_t* ok) {
+    if (nG == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t nM = off[nG];
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t vb = up((size_t)nV * 24), tb = up((size_t)nT * 16), ib = t_ids ? up((size_t)nM * 4) : 0, ob = up((size_t)(nG + 1) * 8),
+                 cb = up((size_t)nG * 4), eb = up((size_t)nG * 8), jb = up((size_t)nG * 24), hb = up((size_t)nG * 72), kb = up((size_t)nG);
+    TWG_TRY(twg_ensure_scratch(c, 0, vb + tb + ib + ob + cb + eb + jb + hb + kb));
+    char* p = (char*)c->dscratch[0];
+    cudaStream_t st = c->streams[0];
+    char* dV = p; p += vb;
+    char* dT = p; p += tb;
+    char* dI = t_ids ? p : nullptr; p += ib;
+    char* dO = p; p += ob;
+    char* dC = p; p += cb;
+    char* dE = p; p += eb;
+    char* dJ = p; p += jb;
+    char* dH = p; p += hb;
+    char* dK = p;
+    TWG_CUDA(c, cudaMemcpyAsync(dV, V, (size_t)nV * 24, cudaMemcpyHostToDevice, st));
+    TWG_CUDA(c, cudaMemcpyAsync(dT, tets, (size_t)nT * 16, cudaMemcpyHostToDevice, st));
+    if (t_ids) TWG_CUDA(c, cudaMemcpyAsync(dI, t_ids, (size_t)nM * 4, cudaMemcpyHostToDevice, st));
+    TWG_CUDA(c, cudaMemcpyAsync(dO, off, (size_t)(nG + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (!energy_only) TWG_CUDA(c, cudaMemcpyAsync(dC, center, (size_t)nG * 4, cudaMemcpyHostToDevice, st));
+    if (energy_only) {
+        TWG_TRY(twg_amips_ring_energy_dev(c, (const double*)dV, nV, (const int32_t*)dT, nT, (const int32_t*)dI, (const uint64_t*)dO, nG,
+                                          (double*)dE, st));
+    } else {
+        TWG_TRY(twg_amips_ring_ejh_dev(c, (const double*)dV, nV, (const int32_t*)dT, nT, (const int32_t*)dI, (const uint64_t*)dO,
+                                       (const int32_t*)dC, nG, (double*)dE, (double*)dJ, (double*)dH, (uint8_t*)dK, st));
+    }
+    TWG_CUDA(c, cudaMemcpyAsync(E, dE, (size_t)nG * 8, cudaMemcpyDeviceToHost, st));
+    if (!energy_only) {
+        TWG_CUDA(c, cudaMemcpyAsync(J3, dJ, (size_t)nG * 24, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaMemcpyAsync(H9, dH, (size_t)nG * 72, cudaMemcpyDeviceToHost, st));
+        if (ok) TWG_CUDA(c, cudaMemcpyAsync(ok, dK, (size_t)nG, cudaMemcpyDeviceToHost, st));
+    }
+    TWG_CUDA(c, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int twg_amips_ring_ejh(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, const int32_t* t_ids,
+                       const uint64_t* off, const int32_t* center, uint64_t nG, double* E, double* J3, double* H9, uint8_t* ok) {
+    TWG_CHECK(c, c && V && tets && off && center && E && J3 && H9, TWG_ERR_INVALID_ARG, "null argument");
+    return ring_host(c, false, V, nV, tets, nT, t_ids, off, center, nG, E, J3, H9, ok);
+}
+
+int twg_amips_ring_energy(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, const int32_t* t_ids,
+                          const uint64_t* off, uint64_t nG, double* E) {
+    TWG_CHECK(c, c && V && tets && off && E, TWG_ERR_INVALID_ARG, "null argument");
+    return ring_host(c, true, V, nV, tets, nT, t_ids, off, nullptr, nG, E, nullptr, nullptr, nullptr);
+}
+
+}  // extern "C"

@@ -1,0 +1,104 @@
+// common.cuh -- context, error handling and small device helpers of libtetwild_gpu (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/tetwild_gpu.h"
+#include "tw_math.cuh"
+
+#define TWG_NUM_STREAMS 3
+
+struct twg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t streams[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
+    // pinned staging (host-buffer entry points): one in + one out slab per stream
+    void* pin_in[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
+    void* pin_out[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
+    size_t pin_in_bytes = 0, pin_out_bytes = 0;
+    // device scratch, grown on demand
+    void* dscratch[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
+    size_t dscratch_bytes[TWG_NUM_STREAMS] = {0, 0, 0};
+    uint64_t launches = 0;
+    mutable char err[512] = {0};
+};
+
+inline int twg_fail(const twg_ctx* c, int code, const char* what, const char* file, int line) {
+    if (c) snprintf(c->err, sizeof(c->err), "%s (%s:%d) code=%d", what, file, line, code);
+    return code ? code : TWG_ERR_INTERNAL;
+}
+
+#define TWG_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) return twg_fail((ctx), (int)e__, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define TWG_CHECK(ctx, cond, code, msg)                                        \
+    do {                                                                       \
+        if (!(cond)) return twg_fail((ctx), (code), (msg), __FILE__, __LINE__); \
+    } while (0)
+
+#define TWG_TRY(expr)              \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// every kernel launch of the library goes through this (gpu_launches accounting for bench.py)
+#define TWG_LAUNCH(ctx, kernel, grid, block, smem, stream, ...)                      \
+    do {                                                                             \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                  \
+        (ctx)->launches++;                                                           \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) return twg_fail((ctx), (int)e__, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
+int twg_ensure_pinned(twg_ctx* c, size_t in_bytes, size_t out_bytes);
+
+// ---- device helpers ----
+#if defined(__CUDACC__)
+__device__ __forceinline__ double ldg_d(const double* p) { return __ldg(p); }
+// 128-bit streaming load / store (read-once inputs, write-once outputs: keep them out of L1)
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream2(double* p, double2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+#endif

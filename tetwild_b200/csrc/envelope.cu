@@ -1,0 +1,308 @@
+// envelope.cu -- batched envelope / nearest-facet queries against a twg_surface (C ABI: include/tetwild_gpu.h).
+//
+// Replaces LocalOperations::isPointOutEnvelop / isFaceOutEnvelop_sampling (src/tetwild/LocalOperations.cpp:1034-1109)
+// and the tree queries behind them (src/tetwild/geogram/mesh_AABB.cpp:381-548).
+//
+// Kernels
+//   env_points_kernel   one thread per query point, stack traversal of the implicit heap, early exit at the first
+//                       facet within eps. The top kTopNodes pair records are staged once per CTA into shared
+//                       memory by ONE 1-D bulk async copy (TMA, cp.async.bulk + mbarrier).
+//   nearest_kernel      same traversal without the eps cut (nearest facet / point / d2).
+//   env_faces_kernel    one warp per candidate face: sampleTriangle runs (sampling.cuh) are dealt to the lanes, each
+//                       lane walks its run sample by sample carrying the previous facet as a hint exactly like the
+//                       reference (:1080-1086); the first OUT sample raises a warp-shared flag and the warp stops.
+#include "surface.cuh"
+#include "sampling.cuh"
+
+namespace {
+
+constexpr uint32_t kTopNodes = 512;  // pair records [0,512) = heap levels 0..8 (children down to level 9): 24 KiB
+constexpr int kEnvThreads = 128;
+
+__device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* top, uint64_t* bar) {
+    const uint32_t topN = S.nLeafP < kTopNodes ? S.nLeafP : kTopNodes;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, topN * (uint32_t)sizeof(NodePair));
+        tma_bulk_g2s(top, S.pairs, topN * (uint32_t)sizeof(NodePair), bar);
+    }
+    mbar_wait(bar, 0);
+    return topN;
+}
+
+__global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, uint64_t n, double eps2,
+                                                                uint8_t* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    NodePair* top = reinterpret_cast<NodePair*>(smraw);
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t topN = stage_top(S, top, &bar);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const tw::V3 p = tw::mk(__ldg(P + 3 * i), __ldg(P + 3 * i + 1), __ldg(P + 3 * i + 2));
+        uint32_t pos;
+        const bool in = twd::in_envelope(S, p, eps2, pos, top, topN);
+        out[i] = in ? 0 : 1;
+    }
+}
+
+__global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, const double* __restrict__ P, uint64_t n, uint32_t* __restrict__ facet,
+                                                             double* __restrict__ nearest, double* __restrict__ d2out) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    NodePair* top = reinterpret_cast<NodePair*>(smraw);
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t topN = stage_top(S, top, &bar);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const tw::V3 p = tw::mk(__ldg(P + 3 * i), __ldg(P + 3 * i + 1), __ldg(P + 3 * i + 2));
+        twd::Nearest b;
+        b.d2 = DBL_MAX; b.s = b.t = 0.0; b.pos = 0; b.deg = false; b.pt_deg = p;
+        twd::nearest_facet(S, p, b, top, topN);
+        if (d2out) d2out[i] = b.d2;
+        if (facet || nearest) {
+            const tw::TriRec r = twd::load_tri(S.tris + b.pos);
+            if (facet) facet[i] = r.facet;
+            if (nearest) {
+                const tw::V3 q = b.deg ? b.pt_deg : tw::tri_nearest_point(r, b.s, b.t);
+                nearest[3 * i] = q.x; nearest[3 * i + 1] = q.y; nearest[3 * i + 2] = q.z;
+            }
+        }
+    }
+}
+
+// one sample of isFaceOutEnvelop_sampling (:1079-1093): hint facet first, then the tree. Returns true if OUT.
+__device__ __forceinline__ bool sample_out(const SurfaceView& S, tw::V3 p, double eps2, uint32_t& prev, const NodePair* top, uint32_t topN) {
+    if (prev != TWG_NO_FACET) {
+        double s, t; tw::V3 nd; bool deg;
+        if (twd::facet_d2(S, prev, p, s, t, nd, deg) <= eps2) return false;
+    }
+    uint32_t pos;
+    if (twd::in_envelope(S, p, eps2, pos, top, topN)) { prev = pos; return false; }
+    return true;
+}
+
+constexpr int kEdgeChunk = 32;  // edge runs are dealt out in chunks of this many samples
+
+__global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
+                                                               uint8_t* __restrict__ out) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    NodePair* top = reinterpret_cast<NodePair*>(smraw);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ volatile int flag[kEnvThreads / 32];
+    const uint32_t topN = stage_top(S, top, &bar);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t f = warp; f < n; f += nwarps) {
+        double t9[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) t9[k] = __ldg(tris + f * 9 + k);
+        if (tw::exact::triangle_is_degenerate(t9, t9 + 3, t9 + 6)) {  // :1048
+            if (lane == 0) out[f] = 0;
+            continue;
+        }
+        tw::SamplePlan P;
+        tw::make_plan(t9, sd, P);
+        // number of rows before the reference's `break` (:197-198): first row whose stop test fires
+        int rows = 0;
+        if (P.kind == 2) {
+            rows = P.M;
+            for (int base = 0; base < P.M; base += 32) {
+                const int m = base + lane + 1;
+                bool stop = false;
+                if (m <= P.M) { tw::RowPlan R; tw::make_row(P, m, R); stop = R.stop; }
+                const unsigned b = __ballot_sync(0xffffffffu, stop);
+                if (b) { rows = base + __ffs(b) - 1; break; }
+            }
+        }
+        if (lane == 0) flag[wib] = 0;
+        __syncwarp();
+        uint32_t prev = TWG_NO_FACET;
+        bool found_out = false;
+        // work items: [0] single vertices, then edge chunks A, B, C, then rows
+        const int cA = (P.nA + kEdgeChunk - 1) / kEdgeChunk, cB = (P.nB + kEdgeChunk - 1) / kEdgeChunk, cC = (P.nC + kEdgeChunk - 1) / kEdgeChunk;
+        const int items = 1 + cA + cB + cC + rows;
+        for (int it = lane; it < items && !found_out; it += 32) {
+            if (flag[wib]) break;
+            int kind, lo, hi;  // kind 0: the single vertices, 1: edge formula, 2: row formula; multipliers [lo, hi)
+            tw::V3 o = P.v0, dir = P.n01;
+            if (it == 0) {
+                kind = 0; lo = (P.kind == 0) ? 0 : 1; hi = 3;
+            } else if (it < 1 + cA + cB + cC) {
+                int c = it - 1;
+                kind = 1;
+                if (c < cA) { lo = c * kEdgeChunk; hi = min(lo + kEdgeChunk, P.nA); }
+                else if (c < cA + cB) { c -= cA; o = P.v1; dir = P.n12; lo = 1 + c * kEdgeChunk; hi = min(lo + kEdgeChunk, P.nB + 1); }
+                else { c -= cA + cB; o = P.v2; dir = P.n20; lo = 1 + c * kEdgeChunk; hi = min(lo + kEdgeChunk, P.nC + 1); }
+            } else {
+                tw::RowPlan R;
+                tw::make_row(P, it - (1 + cA + cB + cC) + 1, R);
+                kind = 2; o = R.v; lo = 0; hi = R.N1 + 1;
+            }
+            for (int k = lo; k < hi; ++k) {
+                if (flag[wib]) break;
+                const tw::V3 p = (kind == 0) ? (k == 0 ? P.v0 : (k == 1 ? P.v1 : P.v2))
+                                             : (kind == 1 ? tw::edge_sample(o, dir, sd, k) : tw::row_sample(o, dir, sd, k));
+                if (sample_out(S, p, eps2, prev, top, topN)) { found_out = true; break; }
+            }
+            if (found_out) flag[wib] = 1;
+        }
+        __syncwarp();
+        const unsigned any = __ballot_sync(0xffffffffu, found_out);
+        if (lane == 0) out[f] = any ? 1 : 0;
+        __syncwarp();
+    }
+}
+
+struct CollectSink {
+    double* out;
+    uint64_t cap, n;
+    __device__ void operator()(tw::V3 p) {
+        if (n < cap) { out[3 * n] = p.x; out[3 * n + 1] = p.y; out[3 * n + 2] = p.z; }
+        ++n;
+    }
+};
+
+__global__ void sample_triangle_kernel(const double* tri9, double sd, double* out, uint64_t cap, uint64_t* count) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double t9[9];
+    for (int k = 0; k < 9; ++k) t9[k] = tri9[k];
+    tw::SamplePlan P;
+    tw::make_plan(t9, sd, P);
+    CollectSink sink{out, cap, 0};
+    tw::enumerate_samples(P, sink);
+    *count = sink.n;
+}
+
+cudaStream_t pick(twg_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->streams[0]; }
+
+unsigned grid_persistent(twg_ctx* c, uint64_t items, int per_block, int ctas_per_sm) {
+    uint64_t b = (items + per_block - 1) / per_block;
+    const uint64_t m = (uint64_t)c->sm_count * ctas_per_sm;
+    if (b > m) b = m;
+    if (b == 0) b = 1;
+    return (unsigned)b;
+}
+
+size_t top_smem(const twg_surface* s) { return (size_t)(s->nLeafP < kTopNodes ? s->nLeafP : kTopNodes) * sizeof(NodePair); }
+
+}  // namespace
+
+extern "C" {
+
+int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, double eps2, uint8_t* dOut, void* stream) {
+    twg_ctx* c = s ? s->ctx : nullptr;
+    TWG_CHECK(c, s && dP && dOut, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, eps2 >= 0.0, TWG_ERR_INVALID_ARG, "eps2 must be >= 0");
+    if (n == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), pick(c, stream), s->view(), dP, n, eps2, dOut);
+    return 0;
+}
+
+int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFacet, double* dNearest, double* dD2, void* stream) {
+    twg_ctx* c = s ? s->ctx : nullptr;
+    TWG_CHECK(c, s && dP, TWG_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), pick(c, stream), s->view(), dP, n, dFacet, dNearest, dD2);
+    return 0;
+}
+
+int twg_envelope_faces_out_dev(twg_surface* s, const double* dTris, uint64_t n, double sd, double eps2, uint8_t* dOut, void* stream) {
+    twg_ctx* c = s ? s->ctx : nullptr;
+    TWG_CHECK(c, s && dTris && dOut, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, eps2 >= 0.0 && sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need eps2 >= 0 and finite sampling_dist > 0");
+    if (n == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, env_faces_kernel, grid_persistent(c, n, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), pick(c, stream), s->view(), dTris, n, sd, eps2, dOut);
+    return 0;
+}
+
+// ---- host-buffer entry points ----
+static int points_host(twg_surface* s, int what, const double* P, uint64_t n, double eps2, uint8_t* out, uint32_t* facet, double* nearest, double* d2) {
+    twg_ctx* c = s->ctx;
+    if (n == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t chunk = 1ull << 22;  // 4 Mi points: 96 MiB in per slot
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const uint64_t cmax = n < chunk ? n : chunk;
+    const size_t pb = up(cmax * 24), ob = up(cmax), fb = up(cmax * 4), nb = up(cmax * 24), db = up(cmax * 8);
+    for (int k = 0; k < TWG_NUM_STREAMS; ++k) TWG_TRY(twg_ensure_scratch(c, k, pb + ob + fb + nb + db));
+    int slot = 0;
+    for (uint64_t b = 0; b < n; b += chunk, slot = (slot + 1) % TWG_NUM_STREAMS) {
+        const uint64_t m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t st = c->streams[slot];
+        char* base = (char*)c->dscratch[slot];
+        double* dP = (double*)base;
+        uint8_t* dO = (uint8_t*)(base + pb);
+        uint32_t* dF = (uint32_t*)(base + pb + ob);
+        double* dN = (double*)(base + pb + ob + fb);
+        double* dD = (double*)(base + pb + ob + fb + nb);
+        TWG_CUDA(c, cudaMemcpyAsync(dP, P + 3 * b, m * 24, cudaMemcpyHostToDevice, st));
+        if (what == 0) {
+            TWG_TRY(twg_envelope_points_out_dev(s, dP, m, eps2, dO, st));
+            TWG_CUDA(c, cudaMemcpyAsync(out + b, dO, m, cudaMemcpyDeviceToHost, st));
+        } else {
+            TWG_TRY(twg_nearest_dev(s, dP, m, facet ? dF : nullptr, nearest ? dN : nullptr, d2 ? dD : nullptr, st));
+            if (facet) TWG_CUDA(c, cudaMemcpyAsync(facet + b, dF, m * 4, cudaMemcpyDeviceToHost, st));
+            if (nearest) TWG_CUDA(c, cudaMemcpyAsync(nearest + 3 * b, dN, m * 24, cudaMemcpyDeviceToHost, st));
+            if (d2) TWG_CUDA(c, cudaMemcpyAsync(d2 + b, dD, m * 8, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int k = 0; k < TWG_NUM_STREAMS; ++k) TWG_CUDA(c, cudaStreamSynchronize(c->streams[k]));
+    return 0;
+}
+
+int twg_envelope_points_out(twg_surface* s, const double* P, uint64_t n, double eps2, uint8_t* out) {
+    twg_ctx* c = s ? s->ctx : nullptr;
+    TWG_CHECK(c, s && P && out, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, eps2 >= 0.0, TWG_ERR_INVALID_ARG, "eps2 must be >= 0");
+    return points_host(s, 0, P, n, eps2, out, nullptr, nullptr, nullptr);
+}
+
+int twg_nearest(twg_surface* s, const double* P, uint64_t n, uint32_t* facet, double* nearest_xyz, double* d2) {
+    twg_ctx* c = s ? s->ctx : nullptr;
+    TWG_CHECK(c, s && P, TWG_ERR_INVALID_ARG, "null argument");
+    return points_host(s, 1, P, n, 0.0, nullptr, facet, nearest_xyz, d2);
+}
+
+int twg_envelope_faces_out(twg_surface* s, const double* tris, uint64_t n, double sd, double eps2, uint8_t* out) {
+    twg_ctx* c = s ? s->ctx : nullptr;
+    TWG_CHECK(c, s && tris && out, TWG_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    TWG_TRY(twg_ensure_scratch(c, 0, up(n * 72) + up(n)));
+    char* base = (char*)c->dscratch[0];
+    cudaStream_t st = c->streams[0];
+    TWG_CUDA(c, cudaMemcpyAsync(base, tris, n * 72, cudaMemcpyHostToDevice, st));
+    TWG_TRY(twg_envelope_faces_out_dev(s, (const double*)base, n, sd, eps2, (uint8_t*)(base + up(n * 72)), st));
+    TWG_CUDA(c, cudaMemcpyAsync(out, base + up(n * 72), n, cudaMemcpyDeviceToHost, st));
+    TWG_CUDA(c, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int twg_sample_triangle(twg_ctx* c, const double* tri9, double sd, double* out_xyz, uint64_t cap, uint64_t* count) {
+    TWG_CHECK(c, c && tri9 && count, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need finite sampling_dist > 0");
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    if (!out_xyz) cap = 0;
+    TWG_TRY(twg_ensure_scratch(c, 0, 256 + 256 + up(cap * 24)));
+    char* base = (char*)c->dscratch[0];
+    cudaStream_t st = c->streams[0];
+    TWG_CUDA(c, cudaMemcpyAsync(base, tri9, 72, cudaMemcpyHostToDevice, st));
+    TWG_LAUNCH(c, sample_triangle_kernel, 1, 32, 0, st, (const double*)base, sd, (double*)(base + 512), cap, (uint64_t*)(base + 256));
+    TWG_CUDA(c, cudaMemcpyAsync(count, base + 256, 8, cudaMemcpyDeviceToHost, st));
+    TWG_CUDA(c, cudaStreamSynchronize(st));
+    const uint64_t m = *count < cap ? *count : cap;
+    if (m) {
+        TWG_CUDA(c, cudaMemcpyAsync(out_xyz, base + 512, m * 24, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+}  // extern "C"

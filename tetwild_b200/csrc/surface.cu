@@ -1,0 +1,225 @@
+// surface.cu -- on-device construction of the envelope structure (replaces the constructor of
+// GEO::MeshFacetsAABBWithEps, src/tetwild/geogram/mesh_AABB.cpp:356-379: Morton reorder :368-370, bbox fill :63-141).
+//
+// Pipeline (all on the device): facet bbox reduction -> 63-bit Morton key of each facet centroid -> radix sort
+// (cub::DeviceRadixSort) -> per-facet TriRec + leaf boxes -> bottom-up union of the implicit heap, one launch per level.
+#include <cub/device/device_radix_sort.cuh>
+#include "surface.cuh"
+
+namespace {
+
+__device__ __forceinline__ unsigned long long enc(double d) {  // order-preserving double -> u64
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__host__ __device__ inline double dec(unsigned long long u) {
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+__global__ void init_bounds_kernel(unsigned long long* bounds) {
+    if (threadIdx.x < 3) bounds[threadIdx.x] = ~0ull;      // min slots
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = 0ull;  // max slots
+}
+
+__global__ void __launch_bounds__(256) bounds_kernel(const double* __restrict__ V, const uint32_t* __restrict__ F, uint32_t nF,
+                                                     unsigned long long* bounds) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double* p = V + 3 * (size_t)F[3 * (size_t)f + k];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], p[c]); hi[c] = fmax(hi[c], p[c]); }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { atomicMin(bounds + c, enc(lo[c])); atomicMax(bounds + 3 + c, enc(hi[c])); }
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread3(unsigned long long v) {
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ V, const uint32_t* __restrict__ F, uint32_t nF,
+                                                     const unsigned long long* __restrict__ bounds, unsigned long long* keys, uint32_t* vals) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    unsigned long long code = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double lo = dec(bounds[c]), hi = dec(bounds[3 + c]);
+        double ctr = (V[3 * (size_t)F[3 * (size_t)f] + c] + V[3 * (size_t)F[3 * (size_t)f + 1] + c] + V[3 * (size_t)F[3 * (size_t)f + 2] + c]) * (1.0 / 3.0);
+        const double ext = hi - lo;
+        double u = ext > 0.0 ? (ctr - lo) / ext : 0.0;
+        u = fmin(fmax(u, 0.0), 1.0);
+        code |= spread3((unsigned long long)(u * 2097151.0)) << c;
+    }
+    keys[f] = code;
+    vals[f] = f;
+}
+
+__device__ __forceinline__ void store_half(NodePair* pairs, uint32_t node /*child index*/, float lx, float ly, float lz, float hx, float hy, float hz) {
+    float* dst = reinterpret_cast<float*>(pairs + (node >> 1)) + (node & 1u) * 6;
+    dst[0] = lx; dst[1] = ly; dst[2] = lz; dst[3] = hx; dst[4] = hy; dst[5] = hz;
+}
+
+__global__ void __launch_bounds__(128) leaf_kernel(const double* __restrict__ V, const uint32_t* __restrict__ F, const uint32_t* __restrict__ order,
+                                                   uint32_t nF, uint32_t nLeafP, tw::TriRec* tris, double* triV, NodePair* pairs) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nLeafP) return;
+    if (j >= nF) {
+        const float inf = __int_as_float(0x7f800000);
+        store_half(pairs, nLeafP + j, inf, inf, inf, -inf, -inf, -inf);
+        return;
+    }
+    const uint32_t f = order[j];
+    double tv[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double* p = V + 3 * (size_t)F[3 * (size_t)f + k];
+        tv[3 * k] = p[0]; tv[3 * k + 1] = p[1]; tv[3 * k + 2] = p[2];
+    }
+    tw::TriRec r;
+    tw::make_trirec(tv, tv + 3, tv + 6, f, r);
+    tris[j] = r;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) triV[(size_t)j * 9 + k] = tv[k];
+    float lo[3], hi[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        lo[c] = __double2float_rd(fmin(fmin(tv[c], tv[3 + c]), tv[6 + c]));
+        hi[c] = __double2float_ru(fmax(fmax(tv[c], tv[3 + c]), tv[6 + c]));
+    }
+    store_half(pairs, nLeafP + j, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
+}
+
+// nodes [first, 2*first): union of their two child boxes -> their slot in the parent record
+__global__ void __launch_bounds__(256) level_kernel(NodePair* pairs, uint32_t first) {
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2u * first) return;
+    const float* s = reinterpret_cast<const float*>(pairs + i);
+    store_half(pairs, i, fminf(s[0], s[6]), fminf(s[1], s[7]), fminf(s[2], s[8]), fmaxf(s[3], s[9]), fmaxf(s[4], s[10]), fmaxf(s[5], s[11]));
+}
+
+int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_t nF, twg_surface** out) {
+    (void)nV;
+    cudaStream_t st = c->streams[0];
+    twg_surface* s = new twg_surface;
+    s->ctx = c;
+    s->nF = nF;
+    uint32_t lp = 2;
+    while (lp < nF) lp <<= 1;
+    s->nLeafP = lp;
+    unsigned long long *bounds = nullptr, *keys = nullptr, *keys2 = nullptr;
+    uint32_t *vals = nullptr, *vals2 = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int rc = 0;
+    auto fail = [&](int code) {
+        cudaFree(bounds); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(tmp);
+        twg_surface_destroy(s);
+        return code;
+    };
+#define B_CUDA(call)                                                                                              \
+    do {                                                                                                          \
+        cudaError_t e__ = (call);                                                                                 \
+        if (e__ != cudaSuccess) return fail(twg_fail(c, (int)e__, cudaGetErrorString(e__), __FILE__, __LINE__)); \
+    } while (0)
+    B_CUDA(cudaMalloc(&s->pairs, sizeof(NodePair) * (size_t)lp));
+    B_CUDA(cudaMalloc(&s->tris, sizeof(tw::TriRec) * (size_t)nF));
+    B_CUDA(cudaMalloc(&s->triV, sizeof(double) * 9 * (size_t)nF));
+    B_CUDA(cudaMalloc(&bounds, 6 * sizeof(unsigned long long)));
+    B_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)nF));
+    B_CUDA(cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)nF));
+    B_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)nF));
+    B_CUDA(cudaMalloc(&vals2, sizeof(uint32_t) * (size_t)nF));
+    B_CUDA(cudaMemsetAsync(s->pairs, 0, sizeof(NodePair) * (size_t)lp, st));
+    init_bounds_kernel<<<1, 32, 0, st>>>(bounds);
+    c->launches++;
+    {
+        unsigned g = (nF + 255) / 256;
+        if (g > (unsigned)c->sm_count * 8) g = c->sm_count * 8;
+        bounds_kernel<<<g, 256, 0, st>>>(dV, dF, nF, bounds);
+        c->launches++;
+        morton_kernel<<<(nF + 255) / 256, 256, 0, st>>>(dV, dF, nF, bounds, keys, vals);
+        c->launches++;
+    }
+    B_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)nF, 0, 63, st));
+    B_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    B_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)nF, 0, 63, st));
+    c->launches += 4;  // cub: histogram + onesweep passes (approximate, library kernels)
+    leaf_kernel<<<(lp + 127) / 128, 128, 0, st>>>(dV, dF, vals2, nF, lp, s->tris, s->triV, s->pairs);
+    c->launches++;
+    for (uint32_t first = lp / 2; first >= 2; first >>= 1) {
+        level_kernel<<<(first + 255) / 256, 256, 0, st>>>(s->pairs, first);
+        c->launches++;
+    }
+    B_CUDA(cudaGetLastError());
+    B_CUDA(cudaStreamSynchronize(st));
+#undef B_CUDA
+    cudaFree(bounds); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(tmp);
+    *out = s;
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+void twg_surface_destroy(twg_surface* s) {
+    if (!s) return;
+    if (s->ctx) cudaSetDevice(s->ctx->device);
+    cudaFree(s->pairs);
+    cudaFree(s->tris);
+    cudaFree(s->triV);
+    delete s;
+}
+
+uint32_t twg_surface_num_facets(const twg_surface* s) { return s ? s->nF : 0; }
+
+int twg_surface_create_dev(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_t nF, twg_surface** out) {
+    TWG_CHECK(c, c && dV && dF && out, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, nF > 0 && nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "surface must have 1 .. 2^31-2 facets");
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    return build(c, dV, nV, dF, nF, out);
+}
+
+int twg_surface_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_surface** out) {
+    TWG_CHECK(c, c && V && F && out, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, nF > 0 && nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "surface must have 1 .. 2^31-2 facets");
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    double* dV = nullptr;
+    uint32_t* dF = nullptr;
+    TWG_CUDA(c, cudaMalloc(&dV, sizeof(double) * 3 * (size_t)nV));
+    cudaError_t e = cudaMalloc(&dF, sizeof(uint32_t) * 3 * (size_t)nF);
+    if (e != cudaSuccess) { cudaFree(dV); return twg_fail(c, (int)e, cudaGetErrorString(e), __FILE__, __LINE__); }
+    int rc = 0;
+    e = cudaMemcpyAsync(dV, V, sizeof(double) * 3 * (size_t)nV, cudaMemcpyHostToDevice, c->streams[0]);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dF, F, sizeof(uint32_t) * 3 * (size_t)nF, cudaMemcpyHostToDevice, c->streams[0]);
+    if (e != cudaSuccess) rc = twg_fail(c, (int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    if (rc == 0) rc = build(c, dV, nV, dF, nF, out);
+    cudaFree(dV);
+    cudaFree(dF);
+    return rc;
+}
+
+}  // extern "C"
