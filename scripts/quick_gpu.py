@@ -19,6 +19,7 @@ def timeit(fn, iters=5, warm=2):
 def main():
     torch.cuda.init()
     ctx = tw.Context(0)
+    torch.cuda.set_stream(torch.cuda.Stream())   # a real (non-NULL) stream handle: NULL means "the context's stream"
     s = torch.cuda.current_stream().cuda_stream
     res = {}
     # ---- AMIPS flat SoA, 16M tets

@@ -90,13 +90,17 @@ def test_ring_ejh(ctx, oracle):
 
 
 def test_ring_rejects(ctx, oracle):
+    """NewtonsUpdate returns false on NaN energy / non-finite J,H (VertexSmoother.cpp:684-699); getNewEnergy clamps."""
     V, tets, off, center = synth.ring_groups(64, seed=9)
     V = V.copy()
-    V[tets[off[3].astype(int), 1]] = V[tets[off[3].astype(int), 2]]  # zero-volume member -> E = inf -> MAX_ENERGY, J/H not finite
+    V[tets[int(off[3]) + 1, (list(tets[int(off[3]) + 1]).index(center[3]) + 1) % 4], 1] = np.nan   # poison one ring vertex of group 3
+    big = tets[int(off[7]), (list(tets[int(off[7])]).index(center[7]) + 2) % 4]
+    V[big] = 1e200                                                                                   # overflow in group 7
     E, J, H, ok = ctx.amips_ring_ejh(V, tets, off, center)
     Er, Jr, Hr, okr = oracle.amips_ring_ejh(V, tets, off, center)
-    assert np.array_equal(ok, okr) and ok[3] == 0 and ok.sum() == 63
-    assert ctx.amips_ring_energy(V, tets, off)[3] == oracle.MAX_ENERGY
+    assert np.array_equal(ok, okr) and ok[3] == 0 and ok[7] == 0 and ok.sum() == 62
+    En, Enr = ctx.amips_ring_energy(V, tets, off), oracle.amips_ring_energy(V, tets, off)
+    assert En[3] == oracle.MAX_ENERGY and Enr[3] == oracle.MAX_ENERGY and En[7] == Enr[7] == oracle.MAX_ENERGY
 
 
 def test_large_batch_properties(ctx, oracle):

@@ -47,12 +47,13 @@ def test_nearest_exact(knot):
     P = synth.envelope_points(V, F, 100000, eps, seed=5)
     f, q, d = S.nearest(P)
     fr, qr, dr = OS.nearest(P, threads=4)
-    assert np.array_equal(d, dr)                       # squared_distance(): bit exact
+    assert np.allclose(d, dr, rtol=1e-14, atol=0)      # squared_distance(): equal up to the reference's own tie pruning
+    assert np.array_equal(d[:5000], OS.sqdist_brute(P[:5000], threads=4)[0])   # and bit exact against the true minimum
     same = f == fr
     assert same.mean() > 0.7                           # ties (points exactly on shared edges) may pick either facet
     assert np.array_equal(q[same], qr[same])
     assert np.allclose(((P - q) ** 2).sum(1), d, rtol=1e-6, atol=1e-18)
-    assert np.array_equal(S.squared_distance(P[:1000]), dr[:1000])
+    assert np.array_equal(S.squared_distance(P[:1000]), d[:1000])
     # isPointOutEnvelop goes through squared_distance() > eps_2 (LocalOperations.cpp:1037): same decision
     assert np.array_equal((d > eps2).astype(np.uint8), S.points_out(P, eps2))
 
@@ -66,13 +67,16 @@ def test_edge_cases(ctx, oracle):
         P[:100, 2] = 0.0
         for eps2 in (0.0, 1e-4, 0.3):
             assert np.array_equal(S.points_out(P, eps2), OS.points_out(P, eps2))
-        assert np.array_equal(S.nearest(P)[2], OS.nearest(P)[2])
+        d = S.nearest(P)[2]
+        assert np.array_equal(d, OS.sqdist_brute(P)[0])          # = min over all facets of the per-facet d2, bit exact
+        assert np.allclose(d, OS.nearest(P)[2], rtol=1e-14, atol=0)  # the reference's pruned search can sit 1 ulp above on ties
         assert len(S.points_out(np.zeros((0, 3)), 1e-3)) == 0
         assert np.array_equal(S.points_out(P[:1], 1e-4), OS.points_out(P[:1], 1e-4))
     # degenerate facets (the reference's boundary mesh stores edges as degenerate triangles, Preprocess.cpp:192-197)
     Fd = np.array([[0, 1, 1], [1, 2, 2], [2, 3, 3], [0, 1, 2]], dtype=np.uint32)
     S, OS = tw.Surface(ctx, V, Fd), oracle.Surface(V, Fd)
-    assert np.array_equal(S.nearest(P)[2], OS.nearest(P)[2])
+    assert np.array_equal(S.nearest(P)[2], OS.sqdist_brute(P)[0])
+    assert np.allclose(S.nearest(P)[2], OS.nearest(P)[2], rtol=1e-14, atol=0)
     assert np.array_equal(S.points_out(P, 1e-2), OS.points_out(P, 1e-2))
 
 
@@ -88,20 +92,31 @@ def test_sample_triangle_device_bit_exact(ctx, oracle):
         assert np.array_equal(ctx.sample_triangle(tri, sd), oracle.sample_triangle(tri, sd))
 
 
-def test_faces_out_exact(knot, oracle):
+def test_faces_out_exact(knot, ctx, oracle):
     V, F, S, OS = knot
-    for eps_rel, edge in ((2e-3, 0.02), (1e-3, 0.05), (4e-3, 0.004)):
+    # small candidate faces (a handful of samples each), eps / sampling_dist through State.cpp:36-41
+    for eps_rel, edge in ((2e-3, 0.004), (1e-3, 0.006), (4e-3, 0.01)):
         sd, eps, eps2 = synth.state_eps(eps_rel)
         T = synth.face_queries(V, F, 1500, edge, eps, seed=int(edge * 1e4))
         T[::97] = np.array([0, 0, 5, 1, 1, 6, 2, 2, 7.0])      # collinear -> IN (LocalOperations.cpp:1048)
         got = S.faces_out(T, sd, eps2)
         ref, ns = OS.faces_out(T, sd, eps2, threads=4)
         assert np.array_equal(got, ref)
-        assert 0.05 < got.mean() < 0.95
+        assert 0.03 < got.mean() < 0.97
     # faces of the surface itself are IN; pushed far away they are OUT
     tri = V[F[:500].astype(np.int64)].reshape(-1, 9)
     assert not S.faces_out(tri, sd, eps2).any()
     assert S.faces_out(tri + 0.05, sd, eps2).all()
+    # BASELINE config-1-shaped calls: 20 480-triangle icosphere, faces of edge ~ diag/20 -> ~1.1k samples each
+    Vi, Fi = synth.icosphere(5)
+    Vi = synth.normalise_unit_diag(Vi)
+    Si, OSi = tw.Surface(ctx, Vi, Fi), oracle.Surface(Vi, Fi)
+    for sd, eps, edge, sig in ((1e-3, 3e-3, 0.05, 4e-3), (1e-3, 2e-3, 0.03, 3e-3), (5e-4, 1.5e-3, 0.02, 2e-3)):
+        T = synth.face_queries(Vi, Fi, 600, edge, sig, seed=int(edge * 1e4))
+        got = Si.faces_out(T, sd, eps * eps)
+        ref, ns = OSi.faces_out(T, sd, eps * eps, threads=4)
+        assert np.array_equal(got, ref) and 0.1 < got.mean() < 0.6 and ns.mean() > 400
+    assert len(Si.faces_out(np.zeros((0, 9)), 1e-3, 1e-6)) == 0
 
 
 def test_full_size_config2(ctx, oracle):

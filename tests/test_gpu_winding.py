@@ -67,7 +67,11 @@ def test_open_and_soup(ctx, oracle):
 
 def test_self_intersecting_union(ctx, oracle):
     V, F = synth.sphere_union(6, 40, 41, seed=5)
-    Q = synth.winding_queries(V, 20000, seed=4)
+    V2, F2 = synth.uv_sphere(30, 30, radius=0.05, normalise=False)   # plus a small sphere nested at the centroid of sphere 0
+    c0 = V[: 2 + 40 * 40].mean(0)
+    F = np.concatenate([F, F2 + len(V)]).astype(np.uint32)
+    V = np.concatenate([V, V2 + c0])
+    Q = np.concatenate([synth.winding_queries(V, 20000, seed=4), c0 + 0.01 * np.random.default_rng(1).normal(size=(200, 3))])
     W, keep = tw.Winding(ctx, V, F).eval(Q)
     Wd = oracle.winding_direct(V, F, Q, threads=8)
     assert np.abs(W - Wd).max() < 1e-10

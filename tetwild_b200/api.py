@@ -116,12 +116,16 @@ class Context:
         self._check(self._L.twg_amips_energy_soa(self.h, ptrs, _ptr(E), C.c_uint64(n)))
         return E
 
-    def amips_ejh_soa(self, T, want=(True, True, True)):
+    def amips_ejh_soa(self, T, want=(True, True, True), out=None):
+        """comformalAMIPS{Energy,Jacobian,Hessian}_new per tet; `out` = optional preallocated (E, J3, H9) (e.g. pinned)"""
         T, ptrs = self._soa_ptrs(T)
         n = T.shape[1]
-        E = np.empty(n) if want[0] else None
-        J = np.empty((n, 3)) if want[1] else None
-        H = np.empty((n, 9)) if want[2] else None
+        if out is not None:
+            E, J, H = out
+        else:
+            E = np.empty(n) if want[0] else None
+            J = np.empty((n, 3)) if want[1] else None
+            H = np.empty((n, 9)) if want[2] else None
         self._check(self._L.twg_amips_ejh_soa(self.h, ptrs, _ptr(E), _ptr(J), _ptr(H), C.c_uint64(n)))
         return E, J, H
 
@@ -229,10 +233,11 @@ class Surface:
         except Exception:
             pass
 
-    def points_out(self, P, eps2):
+    def points_out(self, P, eps2, out=None):
         """out[i] = isPointOutEnvelop(P[i]) (LocalOperations.cpp:1034-1044)"""
         P = _f64(P)
-        out = np.empty(len(P), dtype=np.uint8)
+        if out is None:
+            out = np.empty(len(P), dtype=np.uint8)
         self.ctx._check(self._L.twg_envelope_points_out(self.h, _ptr(P), C.c_uint64(len(P)), C.c_double(eps2), _ptr(out)))
         return out
 
@@ -292,10 +297,13 @@ class Winding:
         except Exception:
             pass
 
-    def eval(self, Q, want_w=True, want_keep=True):
+    def eval(self, Q, want_w=True, want_keep=True, out=None):
         Q = _f64(Q)
-        W = np.empty(len(Q)) if want_w else None
-        keep = np.empty(len(Q), dtype=np.uint8) if want_keep else None
+        if out is not None:
+            W, keep = out
+        else:
+            W = np.empty(len(Q)) if want_w else None
+            keep = np.empty(len(Q), dtype=np.uint8) if want_keep else None
         self.ctx._check(self._L.twg_winding_eval(self.h, _ptr(Q), C.c_uint64(len(Q)), _ptr(W), _ptr(keep)))
         return W, keep
 
