@@ -76,7 +76,9 @@ def test_edge_cases(ctx, oracle):
     Fd = np.array([[0, 1, 1], [1, 2, 2], [2, 3, 3], [0, 1, 2]], dtype=np.uint32)
     S, OS = tw.Surface(ctx, V, Fd), oracle.Surface(V, Fd)
     assert np.array_equal(S.nearest(P)[2], OS.sqdist_brute(P)[0])
-    assert np.allclose(S.nearest(P)[2], OS.nearest(P)[2], rtol=1e-14, atol=0)
+    # an edge stored both as a degenerate facet and as the side of a real triangle evaluates to two d2 values a few ulps
+    # apart; the reference's pruned search keeps whichever it meets first (measured 1.8e-14 relative), the device keeps the min
+    assert np.allclose(S.nearest(P)[2], OS.nearest(P)[2], rtol=1e-12, atol=0)
     assert np.array_equal(S.points_out(P, 1e-2), OS.points_out(P, 1e-2))
 
 
