@@ -45,6 +45,11 @@ def main():
     for name, e2 in (("env_state_eps", eps2), ("env_1e-3", 1e-6)):
         t = timeit(lambda: S.points_out_dev(dP.data_ptr(), n, e2, dO.data_ptr(), s))
         res[name] = dict(ms=t[0], gpts_s=n/t[0]/1e6, out_frac=float(dO.float().mean()))
+    os.environ["TWG_ENVELOPE_SORT"] = "0"
+    S2 = tw.Surface(ctx, V, F)
+    t = timeit(lambda: S2.points_out_dev(dP.data_ptr(), n, eps2, dO.data_ptr(), s))
+    res["env_state_eps_nosort"] = dict(ms=t[0], gpts_s=n/t[0]/1e6)
+    del os.environ["TWG_ENVELOPE_SORT"]
     # sorted points
     t = timeit(lambda: S.nearest_dev(dP.data_ptr(), n, 0, 0, torch.empty(n, device="cuda", dtype=torch.float64).data_ptr(), s), iters=3, warm=1)
     res["nearest"] = dict(ms=t[0], gpts_s=n/t[0]/1e6)
@@ -60,14 +65,12 @@ def main():
     n = int(os.environ.get("QN_WIND", 4_000_000))
     Q = synth.winding_queries(V, n)
     dQ = torch.from_numpy(Q).cuda(); dK = torch.empty(n, device="cuda", dtype=torch.uint8)
-    for tma in ("1", "0"):
-        for srt in ("1", "0"):
-            os.environ["TWG_WINDING_TMA"], os.environ["TWG_WINDING_SORT"] = tma, srt
-            t0 = time.time(); W = tw.Winding(ctx, V, F); bt = time.time()-t0
-            nn = n if srt == "1" else n // 8
-            t = timeit(lambda: W.eval_dev(dQ.data_ptr(), nn, 0, dK.data_ptr(), s), iters=2, warm=1)
-            res["winding_tma%s_sort%s" % (tma, srt)] = dict(ms=t[0], mq_s=nn/t[0]/1e3, build_s=bt, inside=float(dK[:nn].float().mean()), **W.stats())
-            W.close()
+    for leaf in os.environ.get("QN_LEAVES", "32,64,128").split(","):
+        os.environ["TWG_WINDING_LEAF"] = leaf
+        t0 = time.time(); W = tw.Winding(ctx, V, F); bt = time.time()-t0
+        t = timeit(lambda: W.eval_dev(dQ.data_ptr(), n, 0, dK.data_ptr(), s), iters=2, warm=1)
+        res["winding_leaf%s" % leaf] = dict(ms=t[0], mq_s=n/t[0]/1e3, build_s=bt, inside=float(dK.float().mean()), **W.stats())
+        W.close()
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/quick_gpu.json", "w"), indent=1)

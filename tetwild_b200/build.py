@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtetwild_gpu.so")
-SOURCES = ["ctx.cu", "amips.cu", "surface.cu", "envelope.cu", "winding.cu"]
+SOURCES = ["ctx.cu", "qsort.cu", "amips.cu", "surface.cu", "envelope.cu", "winding.cu"]
 HEADERS = ["common.cuh", "tw_math.cuh", "surface.cuh", "sampling.cuh", os.path.join("..", "..", "include", "tetwild_gpu.h")]
 
 NVCC_FLAGS = [
@@ -58,7 +58,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
-    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-ccbin", ccbin, "-Wno-deprecated-gpu-targets", "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd, env=env)
     return LIB
 

@@ -23,6 +23,9 @@ struct twg_ctx {
     // device scratch, grown on demand
     void* dscratch[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
     size_t dscratch_bytes[TWG_NUM_STREAMS] = {0, 0, 0};
+    // Morton-sort scratch (qsort.cu): one per staging stream + one (TWG_SORT_LANE_EXT) for callers' own streams
+    void* dsort[TWG_NUM_STREAMS + 1] = {nullptr, nullptr, nullptr, nullptr};
+    size_t dsort_bytes[TWG_NUM_STREAMS + 1] = {0, 0, 0, 0};
     uint64_t launches = 0;
     mutable char err[512] = {0};
 };
@@ -60,6 +63,14 @@ inline int twg_fail(const twg_ctx* c, int code, const char* what, const char* fi
 
 int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
 int twg_ensure_pinned(twg_ctx* c, size_t in_bytes, size_t out_bytes);
+#define TWG_SORT_LANE_EXT TWG_NUM_STREAMS
+#define TWG_SORT_MIN 4096  /* batches below this are traversed in the caller's order */
+int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out);
+inline int twg_lane_of(const twg_ctx* c, cudaStream_t st) {
+    for (int k = 0; k < TWG_NUM_STREAMS; ++k)
+        if (st == c->streams[k]) return k;
+    return TWG_SORT_LANE_EXT;
+}
 
 // ---- device helpers ----
 #if defined(__CUDACC__)

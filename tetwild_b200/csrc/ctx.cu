@@ -40,6 +40,8 @@ void twg_destroy(twg_ctx* c) {
         if (c->pin_out[i]) cudaFreeHost(c->pin_out[i]);
         if (c->dscratch[i]) cudaFree(c->dscratch[i]);
     }
+    for (int i = 0; i <= TWG_NUM_STREAMS; ++i)
+        if (c->dsort[i]) cudaFree(c->dsort[i]);
     delete c;
 }
 

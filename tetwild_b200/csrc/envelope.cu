@@ -34,27 +34,35 @@ __device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* to
     return topN;
 }
 
-__global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, uint64_t n, double eps2,
-                                                                uint8_t* __restrict__ out) {
+// perm (optional): Morton order of the batch (qsort.cu); lane i handles query perm[i] so that a warp walks one
+// neighbourhood of the tree. A CTA owns a contiguous run of the sorted order (blocked, not grid-strided) for L1 reuse.
+__global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
+                                                                uint64_t n, double eps2, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
     const uint32_t topN = stage_top(S, top, &bar);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const tw::V3 p = tw::mk(__ldg(P + 3 * i), __ldg(P + 3 * i + 1), __ldg(P + 3 * i + 2));
+    const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + kEnvThreads - 1) / kEnvThreads * kEnvThreads;
+    const uint64_t b = (uint64_t)blockIdx.x * per, e = (b + per < n) ? b + per : n;
+    for (uint64_t i = b + threadIdx.x; i < e; i += kEnvThreads) {
+        const uint64_t src = perm ? (uint64_t)__ldg(perm + i) : i;
+        const tw::V3 p = tw::mk(__ldg(P + 3 * src), __ldg(P + 3 * src + 1), __ldg(P + 3 * src + 2));
         uint32_t pos;
         const bool in = twd::in_envelope(S, p, eps2, pos, top, topN);
-        out[i] = in ? 0 : 1;
+        out[src] = in ? 0 : 1;
     }
 }
 
-__global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, const double* __restrict__ P, uint64_t n, uint32_t* __restrict__ facet,
-                                                             double* __restrict__ nearest, double* __restrict__ d2out) {
+__global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm, uint64_t n,
+                                                             uint32_t* __restrict__ facet, double* __restrict__ nearest, double* __restrict__ d2out) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
     const uint32_t topN = stage_top(S, top, &bar);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + kEnvThreads - 1) / kEnvThreads * kEnvThreads;
+    const uint64_t b0 = (uint64_t)blockIdx.x * per, e0 = (b0 + per < n) ? b0 + per : n;
+    for (uint64_t j = b0 + threadIdx.x; j < e0; j += kEnvThreads) {
+        const uint64_t i = perm ? (uint64_t)__ldg(perm + j) : j;
         const tw::V3 p = tw::mk(__ldg(P + 3 * i), __ldg(P + 3 * i + 1), __ldg(P + 3 * i + 2));
         twd::Nearest b;
         b.d2 = DBL_MAX; b.s = b.t = 0.0; b.pos = 0; b.deg = false; b.pt_deg = p;
@@ -197,7 +205,10 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     TWG_CHECK(c, eps2 >= 0.0, TWG_ERR_INVALID_ARG, "eps2 must be >= 0");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), pick(c, stream), s->view(), dP, n, eps2, dOut);
+    cudaStream_t st = pick(c, stream);
+    const uint32_t* perm = nullptr;
+    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm));
+    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), st, s->view(), dP, perm, n, eps2, dOut);
     return 0;
 }
 
@@ -206,7 +217,10 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     TWG_CHECK(c, s && dP, TWG_ERR_INVALID_ARG, "null argument");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), pick(c, stream), s->view(), dP, n, dFacet, dNearest, dD2);
+    cudaStream_t st = pick(c, stream);
+    const uint32_t* perm = nullptr;
+    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm));
+    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), st, s->view(), dP, perm, n, dFacet, dNearest, dD2);
     return 0;
 }
 

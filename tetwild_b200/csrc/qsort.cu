@@ -1,0 +1,110 @@
+// qsort.cu -- Morton ordering of a query batch on the device (shared by the envelope and winding kernels).
+//
+// Both traversals are one-query-per-lane; a warp only runs at full SIMT width when its 32 queries take the same path
+// through the hierarchy and touch the same cache lines, so every large batch is first ordered along a 30-bit Morton
+// curve over its own bounding box: bbox reduction -> key kernel -> cub::DeviceRadixSort (keys + original indices).
+// The kernels then read P[perm[i]] and scatter their 1-byte / 8-byte results to the caller's positions.
+// The reference gets the same effect for free: its samples come out of sampleTriangle in spatial order and it passes
+// the previous facet as a hint (LocalOperations.cpp:1078-1086).
+#include <cub/device/device_radix_sort.cuh>
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ unsigned long long enc(double d) {  // order-preserving double -> u64
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec(unsigned long long u) {
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+__global__ void qinit_kernel(unsigned long long* bounds) {
+    if (threadIdx.x < 3) bounds[threadIdx.x] = ~0ull;
+    else if (threadIdx.x < 6) bounds[threadIdx.x] = 0ull;
+}
+__global__ void __launch_bounds__(256) qbounds_kernel(const double* __restrict__ Q, uint64_t n, unsigned long long* bounds) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    // flat coalesced sweep over the 3n doubles; component = index % 3
+    const uint64_t tot = 3 * n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double x = __ldg(Q + i);
+        const int c = (int)(i % 3);
+        if (isfinite(x)) { lo[c] = fmin(lo[c], x); hi[c] = fmax(hi[c], x); }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { atomicMin(bounds + c, enc(lo[c])); atomicMax(bounds + 3 + c, enc(hi[c])); }
+    }
+}
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void __launch_bounds__(256) qkeys_kernel(const double* __restrict__ Q, uint64_t n, const unsigned long long* __restrict__ bounds,
+                                                    uint32_t* keys, uint32_t* vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t code = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double lo = dec(bounds[c]), hi = dec(bounds[3 + c]);
+        const double ext = hi - lo;
+        const double x = __ldg(Q + 3 * i + c);
+        double u = (ext > 0.0 && isfinite(x)) ? (x - lo) / ext : 0.0;
+        u = fmin(fmax(u, 0.0), 1.0);
+        code |= spread10((uint32_t)(u * 1023.0)) << c;
+    }
+    keys[i] = code;
+    vals[i] = (uint32_t)i;
+}
+
+}  // namespace
+
+// perm_out[i] = index (in the caller's order) of the i-th point along the Morton curve. `lane` selects one of the
+// TWG_NUM_STREAMS + 1 sort scratch buffers of the context (one per staging stream + one for external streams).
+int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out) {
+    TWG_CHECK(c, n < 0xffffffffull, TWG_ERR_INVALID_ARG, "at most 2^32-2 queries per call");
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t tmp_bytes = 0;
+    TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                (int)n, 0, 30, st));
+    const size_t kb = up(n * 4);
+    const size_t need = 256 + 4 * kb + up(tmp_bytes);
+    if (c->dsort_bytes[lane] < need) {
+        if (c->dsort[lane]) {
+            TWG_CUDA(c, cudaStreamSynchronize(st));
+            TWG_CUDA(c, cudaFree(c->dsort[lane]));
+            c->dsort[lane] = nullptr;
+            c->dsort_bytes[lane] = 0;
+        }
+        const size_t want = need + need / 8;
+        TWG_CUDA(c, cudaMalloc(&c->dsort[lane], want));
+        c->dsort_bytes[lane] = want;
+    }
+    char* base = (char*)c->dsort[lane];
+    unsigned long long* bounds = (unsigned long long*)base;
+    uint32_t *keys = (uint32_t*)(base + 256), *keys2 = (uint32_t*)(base + 256 + kb), *vals = (uint32_t*)(base + 256 + 2 * kb),
+             *vals2 = (uint32_t*)(base + 256 + 3 * kb);
+    void* tmp = base + 256 + 4 * kb;
+    TWG_LAUNCH(c, qinit_kernel, 1, 32, 0, st, bounds);
+    uint64_t g = (3 * n + 255) / 256;
+    if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+    TWG_LAUNCH(c, qbounds_kernel, (unsigned)g, 256, 0, st, dP, n, bounds);
+    TWG_LAUNCH(c, qkeys_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, n, bounds, keys, vals);
+    TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 30, st));
+    c->launches += 5;  // cub: histogram + exclusive-sum + one onesweep pass per 8 key bits (library kernels)
+    *perm_out = vals2;
+    return 0;
+}

@@ -126,6 +126,10 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
     twg_surface* s = new twg_surface;
     s->ctx = c;
     s->nF = nF;
+    {
+        const char* e = getenv("TWG_ENVELOPE_SORT");
+        s->no_sort = e && e[0] == '0';
+    }
     uint32_t lp = 2;
     while (lp < nF) lp <<= 1;
     s->nLeafP = lp;

@@ -32,6 +32,7 @@ struct twg_surface {
     NodePair* pairs = nullptr;
     tw::TriRec* tris = nullptr;
     double* triV = nullptr;
+    bool no_sort = false;  // TWG_ENVELOPE_SORT=0: traverse batches in the caller's order (profiling aid)
     SurfaceView view() const { return SurfaceView{pairs, tris, triV, nF, nLeafP}; }
 };
 
@@ -77,45 +78,101 @@ __device__ __forceinline__ double facet_d2(const SurfaceView& S, uint32_t pos, t
     return tw::tri_sqdist_degenerate(p, tv, near_deg);
 }
 
+// Conservative single-precision box test. The query point is bracketed by two floats (p_lo <= p <= p_hi), every
+// operation is rounded DOWN, so the result is a rigorous lower bound of the true squared distance from p to the
+// (outward-rounded) box -- and the box contains every facet below it. A subtree is therefore never skipped when it
+// holds a facet with d2 <= eps2 (thr = eps2 rounded UP to float); the bound merely admits a few more boxes than the
+// exact double test would (relative slack ~1e-7). FP32 runs at twice the FP64 rate on B200 and leaves the FP64
+// pipe to the leaf arithmetic, which must stay bit-identical to the reference.
+struct PointF {
+    float lx, ly, lz, hx, hy, hz;
+};
+__device__ __forceinline__ PointF bracket(tw::V3 p) {
+    PointF q;
+    q.lx = __double2float_rd(p.x); q.ly = __double2float_rd(p.y); q.lz = __double2float_rd(p.z);
+    q.hx = __double2float_ru(p.x); q.hy = __double2float_ru(p.y); q.hz = __double2float_ru(p.z);
+    return q;
+}
+__device__ __forceinline__ float box_d2_lb(const PointF& q, float lx, float ly, float lz, float hx, float hy, float hz) {
+    const float dx = fmaxf(fmaxf(__fsub_rd(lx, q.hx), __fsub_rd(q.lx, hx)), 0.0f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(ly, q.hy), __fsub_rd(q.ly, hy)), 0.0f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(lz, q.hz), __fsub_rd(q.lz, hz)), 0.0f);
+    return __fmaf_rd(dz, dz, __fmaf_rd(dy, dy, __fmul_rd(dx, dx)));
+}
+
 // Is some facet within sqrt(eps2) of p?  (facet_in_envelope_recursive, mesh_AABB.cpp:482-548: stop at the first
-// facet with d2 <= eps2, never enter a box farther than eps.)  top/topN: pair records [0, topN) staged in shared memory.
+// facet with d2 <= eps2, never enter a box farther than eps.)
+//
+// 8-wide traversal of the implicit binary heap: the boxes of the eight descendants 8i .. 8i+7 of node i (three levels
+// down) are the four CONSECUTIVE pair records 4i .. 4i+3 = one 192-byte run, fetched with twelve independent 128-bit
+// loads. A query near the surface therefore makes ceil(depth / 3) dependent memory round trips instead of depth
+// (6 instead of 18 for 200k facets; the first three come from the shared-memory copy of the top of the tree), which
+// is what bounds a traversal whose arithmetic per node is ~100 FP32 instructions. top/topN: pair records [0, topN)
+// staged in shared memory.
 __device__ __forceinline__ bool in_envelope(const SurfaceView& S, tw::V3 p, double eps2, uint32_t& hit_pos, const NodePair* top, uint32_t topN) {
-    const double thr = eps2 * kSlack;
-    uint32_t stack[32];
-    int sp = 0;
-    uint32_t node = 1;
+    const float thr = __double2float_ru(eps2);
+    const PointF q = bracket(p);
     const uint32_t leaf0 = S.nLeafP;
-    for (;;) {
-        NodePair np = (node < topN) ? top[node] : load_pair(S.pairs + node);
-        const double dl = box_d2(p.x, p.y, p.z, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
-        const double dr = box_d2(p.x, p.y, p.z, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
-        const bool hl = dl <= thr, hr = dr <= thr;
-        const uint32_t cl = 2u * node;
-        if (cl >= leaf0) {
-            const bool lfirst = !(hr && dr < dl);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const bool left = (k == 0) ? lfirst : !lfirst;
-                const uint32_t pos = (left ? cl : cl + 1u) - leaf0;
-                if ((left ? hl : hr) && pos < S.nF) {
-                    double s, t; tw::V3 nd; bool deg;
-                    const double d2 = facet_d2(S, pos, p, s, t, nd, deg);
-                    if (d2 <= eps2) { hit_pos = pos; return true; }
-                }
-            }
-        } else if (hl || hr) {
-            if (hl && hr) {
-                const bool lnear = dl <= dr;
-                stack[sp++] = lnear ? cl + 1u : cl;
-                node = lnear ? cl : cl + 1u;
-            } else {
-                node = hl ? cl : cl + 1u;
+    uint32_t stack[64];
+    int sp = 0;
+    // the heap has log2(leaf0) levels below the root; start at the level that leaves a multiple of three below it
+    {
+        const int k = 31 - __clz(leaf0);
+        const int r = k % 3;
+        const uint32_t first = 1u << r;
+        for (uint32_t i = 0; i < first; ++i) stack[sp++] = first + i;  // <= 4 subtrees, entered without a box test
+    }
+    while (sp > 0) {
+        const uint32_t node = stack[--sp];
+        if (node >= leaf0) {  // only when the whole tree has fewer than three levels
+            const uint32_t pos = node - leaf0;
+            if (pos < S.nF) {
+                double s, t; tw::V3 nd; bool deg;
+                if (facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { hit_pos = pos; return true; }
             }
             continue;
         }
-        if (sp == 0) return false;
-        node = stack[--sp];
+        const uint32_t c0 = 8u * node;       // first descendant three levels down
+        const uint32_t pr = 4u * node;       // its pair record
+        float d[8];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const NodePair np = (pr + 3u < topN) ? top[pr + h] : load_pair(S.pairs + pr + h);
+            d[2 * h] = box_d2_lb(q, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
+            d[2 * h + 1] = box_d2_lb(q, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
+        }
+        if (c0 >= leaf0) {
+            // descendants are facets: test the admitted ones, nearest box first
+            uint32_t mask = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) mask |= (d[c] <= thr) ? (1u << c) : 0u;
+            while (mask) {
+                int best = -1;
+                float bd = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (((mask >> c) & 1u) && (best < 0 || d[c] < bd)) { best = c; bd = d[c]; }
+                mask &= ~(1u << best);
+                const uint32_t pos = c0 + (uint32_t)best - leaf0;
+                if (pos < S.nF) {
+                    double s, t; tw::V3 nd; bool deg;
+                    if (facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { hit_pos = pos; return true; }
+                }
+            }
+        } else {
+            // push the admitted subtrees, the nearest one last so that it is popped first
+            int best = -1;
+            float bd = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (d[c] <= thr && (best < 0 || d[c] < bd)) { best = c; bd = d[c]; }
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                if (d[c] <= thr && c != best && sp < 63) stack[sp++] = c0 + (uint32_t)c;
+            if (best >= 0) stack[sp++] = c0 + (uint32_t)best;
+        }
     }
+    return false;
 }
 
 struct Nearest {
