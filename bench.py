@@ -29,15 +29,18 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-FULL = {"envelope": 10_000_000, "amips": 50_000_000, "winding": 100_000_000}
-UNIT = {"envelope": "points/s", "amips": "tets/s", "winding": "queries/s"}
-METRIC = {"envelope": "envelope points/s", "amips": "AMIPS E+J+H tet-evals/s", "winding": "winding-number queries/s"}
+FULL = {"envelope": 10_000_000, "amips": 50_000_000, "amips_ring": 50_000_000, "winding": 100_000_000}
+UNIT = {"envelope": "points/s", "amips": "tets/s", "amips_ring": "tets/s", "winding": "queries/s"}
+METRIC = {"envelope": "envelope points/s", "amips": "AMIPS E+J+H tet-evals/s", "amips_ring": "AMIPS one-ring E+J+H tet-evals/s",
+          "winding": "winding-number queries/s"}
 WORKLOAD = {
     "envelope": "C2: %d sampled points vs 200000-triangle (2,3) torus knot, eps_rel=1e-3 -> eps_2=(0.42265e-3)^2 (State.cpp:36-41)",
     "amips": "C3: %d random non-degenerate tets, flat SoA (12 arrays), E+J[3]+H[9] per tet, FP64",
+    "amips_ring": "C3 smoothing-candidate layout: %d random non-degenerate tets in one-rings of k~U{12..36} around a centre vertex (indexed gather, centre rotated to slot 0), E+J[3]+H[9] per ring (NewtonsUpdate), FP64",
     "winding": "C4: %d centroids uniform in 1.2x bbox vs 1001112-triangle closed noisy UV sphere, keep = W > 0.5",
 }
-ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "winding": 25.0}  # algorithmic HBM bytes per unit
+# algorithmic HBM bytes per unit (ring: 16 B indices + 72 B gathered vertices + 128 B of per-ring data / 24)
+ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "amips_ring": 93.0, "winding": 25.0}
 
 
 def peaks():
@@ -134,7 +137,7 @@ def envelope_points_fast(V, F, n, eps, seed):
     return np.ascontiguousarray(P[rng.permutation(n)])
 
 
-def tets_on_device(n, seed, device):
+def tets_on_device(n, seed, device, unit=False):
     """C3 generator on the GPU (same recipe as synth.random_tets: regular tet + N(0,0.15), random rotation, log-uniform
     scale 1e-3..1e3, translation U(-10,10)*scale; inverted draws are mirrored, (near-)flat draws replaced)."""
     import torch
@@ -158,11 +161,52 @@ def tets_on_device(n, seed, device):
                          torch.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], 1),
                          torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)], 1)
         X = torch.einsum("mij,mvj->mvi", R, X)
-        s = torch.exp(torch.empty((m, 1, 1), device=device, dtype=torch.float64).uniform_(math.log(1e-3), math.log(1e3), generator=g))
-        t = torch.empty((m, 1, 3), device=device, dtype=torch.float64).uniform_(-10, 10, generator=g)
-        X = X * s + t * s
+        if not unit:
+            s = torch.exp(torch.empty((m, 1, 1), device=device, dtype=torch.float64).uniform_(math.log(1e-3), math.log(1e3), generator=g))
+            t = torch.empty((m, 1, 3), device=device, dtype=torch.float64).uniform_(-10, 10, generator=g)
+            X = X * s + t * s
         out[:, b:b + m] = X.reshape(m, 12).t()
     return out
+
+
+def rings_on_device(n_tets, seed, device):
+    """C3 ring layout on the GPU (same recipe as synth.ring_groups): returns V[nV,3] f64, tets[nT,4] i32, off[nG+1] u64 (as
+    int64 storage), center[nG] i32. Every tet is CGAL-POSITIVE in its stored order; the centre sits at a random slot."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed + 1)
+    n_groups = max(1, n_tets // 24)
+    k = torch.randint(12, 37, (n_groups,), generator=g, device=device)
+    # trim / pad the last groups so that the total is exactly n_tets
+    off = torch.zeros(n_groups + 1, dtype=torch.int64, device=device)
+    off[1:] = torch.cumsum(k, 0)
+    ng = int(torch.searchsorted(off, torch.tensor([n_tets], device=device), right=False).item())
+    ng = max(1, min(ng, n_groups))
+    off = off[:ng + 1].clone()
+    off[ng] = n_tets
+    if ng > 1 and off[ng] <= off[ng - 1]:
+        ng -= 1
+        off = off[:ng + 1].clone()
+        off[ng] = n_tets
+    n_groups = ng
+    kk = off[1:] - off[:-1]
+    # every ring has ONE scale and position (log-uniform 1e-3..1e3, centre U(-10,10)*scale), like a one-ring of a real mesh:
+    # its member tets are perturbed regular tets of that size glued at the centre vertex
+    X = tets_on_device(n_tets, seed + 2, device, unit=True).t().contiguous().view(n_tets, 4, 3)
+    gi = torch.repeat_interleave(torch.arange(n_groups, device=device), kk)
+    sg = torch.exp(torch.empty((n_groups, 1), device=device, dtype=torch.float64).uniform_(math.log(1e-3), math.log(1e3), generator=g))
+    cen = torch.empty((n_groups, 3), device=device, dtype=torch.float64).uniform_(-10, 10, generator=g) * sg
+    X = (X - X[:, :1]) * sg[gi][:, None, :] + cen[gi][:, None, :]
+    V = torch.cat([cen, X[:, 1:].reshape(-1, 3)], 0).contiguous()
+    base = n_groups + 3 * torch.arange(n_tets, device=device, dtype=torch.int64)
+    tets = torch.stack([gi, base, base + 1, base + 2], 1)
+    rot = torch.randint(0, 4, (n_tets,), generator=g, device=device)
+    odd = (rot % 2) == 1
+    t2 = tets.clone()
+    t2[odd, 2], t2[odd, 3] = tets[odd, 3], tets[odd, 2]
+    idx = (torch.arange(4, device=device)[None, :] - rot[:, None]) % 4  # out[j] = t2[(j - rot) % 4]  (np.roll by rot)
+    out = torch.gather(t2, 1, idx).to(torch.int32).contiguous()
+    del X
+    return V, out, off.contiguous(), torch.arange(n_groups, device=device, dtype=torch.int32)
 
 
 # ------------------------------------------------------------------------------------------------- reference arm
@@ -199,6 +243,17 @@ def cpu_rate(part, n_full, threads, budget_s=8.0):
         T = synth.random_tets(m, seed=7)
         t = time.perf_counter(); fn(T); dt = time.perf_counter() - t
         return m / dt, kind, "%d of %d tets, %s, OpenMP over tets" % (m, n_full, what)
+    if part == "amips_ring":
+        # NewtonsUpdate over one-rings (VertexSmoother.cpp:627-702): per member tet the reference's own E, J, H text
+        m = int(min(n_full, 4_000_000))
+        V, tets, off, cen = synth.ring_groups(max(1, m // 24), seed=7, scale_lo=0.1, scale_hi=10.0)
+        nt = int(off[-1])
+        fn = O.ref_amips_ring_ejh if have_ref else O.amips_ring_ejh
+        kind = "reference" if have_ref else "port"
+        fn(V, tets, off[:1001], cen[:1000], threads=threads)
+        t = time.perf_counter(); fn(V, tets, off, cen, threads=threads); dt = time.perf_counter() - t
+        what = "NewtonsUpdate restated around the reference's own LocalOperations.cpp:28-291 E/J/H text (oracle/ref_wrap.cpp)" if have_ref else "oracle port of NewtonsUpdate"
+        return nt / dt, kind, "%d of %d tets in %d one-rings, %s, OpenMP over rings" % (nt, n_full, len(cen), what)
     if part == "winding":
         V, F = sphere_surface()
         WT = O.WindingTree(V, F)
@@ -371,6 +426,37 @@ def run_gpu(args, parts):
             res.update({"h2d": n * 96, "d2h": n * 104, "extra": {"parity_vs_reference_text": mism}})
             res["config"]["l2"] = "inputs larger than L2: 4.8 GB read + 5.2 GB written per step"
             del dT, dE, dJ, dH, hT, hE, hJ, hH
+        elif part == "amips_ring":
+            dV, dT4, dOff, dCen = rings_on_device(n, 7 + rank, dev)
+            nG, nV = int(dCen.numel()), int(dV.shape[0])
+            dE = torch.empty(nG, device=dev, dtype=torch.float64)
+            dJ = torch.empty((nG, 3), device=dev, dtype=torch.float64)
+            dH = torch.empty((nG, 9), device=dev, dtype=torch.float64)
+            dOk = torch.empty(nG, device=dev, dtype=torch.uint8)
+            step = lambda: ctx.amips_ring_ejh_dev(dV.data_ptr(), nV, dT4.data_ptr(), n, 0, dOff.data_ptr(), dCen.data_ptr(), nG, dE.data_ptr(),  # noqa: E731
+                                                  dJ.data_ptr(), dH.data_ptr(), dOk.data_ptr(), sh)
+            ms, kms, launches, win = timed(step)
+            hV, hT4, hOff, hCen = dV.cpu().pin_memory(), dT4.cpu().pin_memory(), dOff.cpu().pin_memory(), dCen.cpu().pin_memory()
+            e2e_s = e2e_timed(lambda: ctx.amips_ring_ejh(hV.numpy(), hT4.numpy(), hOff.numpy().view(np.uint64), hCen.numpy()))
+            mism = None
+            if rank == 0:
+                gsel = np.random.default_rng(5).choice(nG, min(nG, 4000), replace=False)
+                offs = hOff.numpy()
+                mem = np.concatenate([np.arange(offs[a], offs[a + 1]) for a in gsel])
+                soff = np.zeros(len(gsel) + 1, dtype=np.uint64)
+                soff[1:] = np.cumsum(offs[gsel + 1] - offs[gsel])
+                ring_ref = O.ref_amips_ring_ejh if O.ref_available() else O.amips_ring_ejh
+                Eo, Jo, Ho, oko = ring_ref(hV.numpy(), hT4.numpy(), soff, hCen.numpy()[gsel], t_ids=mem.astype(np.int32), threads=O.max_threads())
+                got = (dE.cpu().numpy()[gsel], dJ.cpu().numpy()[gsel], dH.cpu().numpy()[gsel])
+                eE = np.abs(got[0] - Eo) / np.abs(Eo)
+                eJ = np.abs(got[1] - Jo).max(1) / np.abs(Jo).max(1)
+                eH = np.abs(got[2] - Ho).max(1) / np.abs(Ho).max(1)
+                mism = {"max_rel_err_E": float(eE.max()), "max_rel_err_J_normwise": float(eJ.max()), "max_rel_err_H_normwise": float(eH.max()),
+                        "ok_flag_mismatches": int((dOk.cpu().numpy()[gsel] != oko).sum()), "rings_checked": int(len(gsel))}
+            res.update({"h2d": nV * 24 + n * 16 + (nG + 1) * 8 + nG * 4, "d2h": nG * 105,
+                        "extra": {"rings": nG, "vertices": nV, "parity_vs_oracle": mism}})
+            res["config"]["l2"] = "inputs larger than L2: %.1f GB of vertices + %.1f GB of indices gathered per step" % (nV * 24 / 1e9, n * 16 / 1e9)
+            del dV, dT4, dOff, dCen, dE, dJ, dH, dOk, hV, hT4, hOff, hCen
         elif part == "winding":
             V, F = sphere_surface()
             t0 = time.perf_counter()
@@ -417,8 +503,13 @@ def run_gpu(args, parts):
         h = results[head]
         traffic = load_ncu_traffic()
         for p in parts:
-            if p in traffic:
-                results[p]["roofline"]["traffic"] = traffic[p]
+            t = traffic.get(p)
+            if t:  # dram bytes per launch measured by ncu at t["units"] units, scaled to this launch's size
+                n_p = max(1000, int(FULL[p] * args.scale))
+                results[p]["roofline"]["traffic"] = t["dram_bytes"] * n_p / t["units"]
+                results[p]["roofline"]["traffic_source"] = "%s (ncu --set full, dram__bytes_read+write, n=%d, scaled per unit)" % (t["file"], t["units"])
+                if "fp64_pipe_pct" in t:
+                    results[p]["roofline"]["fp64_pipe_active_pct"] = t["fp64_pipe_pct"]
         out = {"metric": h["metric"], "value": h["value"], "unit": h["unit"], "n_gpus": world, "steps": K, "warmup": Wm,
                "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": dict(h["config"], parallelism="replicated surface, batches split by rank, NCCL all_gather of decisions" if world > 1 else "single GPU"),
@@ -446,7 +537,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--parts", default="envelope,amips,winding")
+    ap.add_argument("--parts", default="envelope,amips,amips_ring,winding")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full BASELINE.json batch sizes (1.0 = as named)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=8.0)

@@ -309,6 +309,19 @@ def ref_amips_ejh_soa(T, threads=1, want=(True, True, True)):
     return E, J, H
 
 
+def ref_amips_ring_ejh(V, tets, group_off, center, t_ids=None, threads=1):
+    """NewtonsUpdate over many one-rings through the reference's own E / J / H text (oracle/ref_wrap.cpp)"""
+    V, tets = _f64(V), _i32(tets)
+    off = np.ascontiguousarray(group_off, dtype=np.uint64)
+    center = _i32(center)
+    tid = _i32(t_ids) if t_ids is not None else None
+    g = center.shape[0]
+    E, J, H, ok = np.empty(g), np.empty((g, 3)), np.empty((g, 9)), np.empty(g, dtype=np.uint8)
+    ref().ref_amips_ring_ejh(_p(V, _dp), _p(tets, _i32p), _p(tid, _i32p), _p(off, _u64p), _p(center, _i32p), C.c_uint64(g),
+                             _p(E, _dp), _p(J, _dp), _p(H, _dp), _p(ok, _u8p), C.c_int(threads))
+    return E, J, H, ok
+
+
 def ref_sample_triangle(tri, sampling_dist):
     t = _f64(tri).reshape(9)
     n = ref().ref_sample_triangle(_p(t, _dp), C.c_double(sampling_dist), None, C.c_uint64(0))

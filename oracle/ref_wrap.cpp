@@ -48,6 +48,40 @@ void ref_amips_ejh_soa(const double* const* Ts, double* E, double* J3, double* H
     }
 }
 
+// VertexSmoother::NewtonsUpdate (VertexSmoother.cpp:627-702) over many one-rings, restated around the reference's own
+// E / J / H text: gather the member tet, rotate the centre vertex to slot 0 (:640-651), add the three results (:652-672),
+// apply the acceptance rules (:680-699). OpenMP over rings (the reference itself runs one ring at a time).
+void ref_amips_ring_ejh(const double* V, const int32_t* tets4, const int32_t* t_ids, const uint64_t* off, const int32_t* center, uint64_t nG,
+                        double* E, double* J3, double* H9, uint8_t* ok, int threads) {
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads > 0 ? threads : 1)
+    for (int64_t g = 0; g < (int64_t)nG; ++g) {
+        double e = 0, J[3] = {0, 0, 0}, H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (uint64_t k = off[g]; k < off[g + 1]; ++k) {
+            const int32_t* t = tets4 + 4 * (size_t)(t_ids ? t_ids[k] : (int64_t)k);
+            int start = 0;
+            for (int j = 0; j < 4; ++j)
+                if (t[j] == center[g]) { start = j; break; }
+            double T[12], j3[3], h9[9];
+            for (int j = 0; j < 4; ++j)
+                for (int c = 0; c < 3; ++c) T[3 * j + c] = V[3 * (size_t)t[(start + j) % 4] + c];
+            e += ref_amips_energy(T);
+            ref_amips_jacobian(T, j3);
+            ref_amips_hessian(T, h9);
+            for (int c = 0; c < 3; ++c) J[c] += j3[c];
+            for (int c = 0; c < 9; ++c) H[c] += h9[c];
+        }
+        bool good = true;
+        if (std::isinf(e)) e = 1e50;
+        if (std::isnan(e) || e <= 0) good = false;
+        for (int c = 0; c < 3; ++c) if (!std::isfinite(J[c])) good = false;
+        for (int c = 0; c < 9; ++c) if (!std::isfinite(H[c])) good = false;
+        E[g] = e;
+        for (int c = 0; c < 3; ++c) J3[3 * g + c] = J[c];
+        for (int c = 0; c < 9; ++c) H9[9 * g + c] = H[c];
+        if (ok) ok[g] = good;
+    }
+}
+
 uint64_t ref_sample_triangle(const double* tri9, double sampling_dist, double* out_xyz, uint64_t cap) {
     std::array<GEO::vec3, 3> vs;
     for (int i = 0; i < 3; ++i) vs[i] = GEO::vec3(tri9[3 * i], tri9[3 * i + 1], tri9[3 * i + 2]);

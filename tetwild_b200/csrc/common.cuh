@@ -65,7 +65,8 @@ int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
 int twg_ensure_pinned(twg_ctx* c, size_t in_bytes, size_t out_bytes);
 #define TWG_SORT_LANE_EXT TWG_NUM_STREAMS
 #define TWG_SORT_MIN 4096  /* batches below this are traversed in the caller's order */
-int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out);
+int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box = nullptr,
+                    const double** sorted_out = nullptr);
 inline int twg_lane_of(const twg_ctx* c, cudaStream_t st) {
     for (int k = 0; k < TWG_NUM_STREAMS; ++k)
         if (st == c->streams[k]) return k;

@@ -16,11 +16,15 @@
 
 namespace {
 
-constexpr uint32_t kTopNodes = 512;  // pair records [0,512) = heap levels 0..8 (children down to level 9): 24 KiB
+// Pair records [0, kTopNodes) (the top of the heap) are staged in shared memory. Measured on B200 (10 M points, 200 k
+// facets): 8 records 2.45, 64 records 2.49, 512 records (24 KiB) 2.37 G points/s -- the L1 already holds the hot top of
+// the tree, and shared memory beyond a few KiB only costs occupancy. Default: 64 records = heap levels 0..5 = 3 KiB.
+constexpr uint32_t kTopNodesMax = 512;
+static uint32_t kTopNodes = [] { const char* e = getenv("TWG_ENV_TOP"); uint32_t v = e ? (uint32_t)atoi(e) : 64u; return v > kTopNodesMax ? kTopNodesMax : (v < 4 ? 4 : v); }();
 constexpr int kEnvThreads = 128;
 
 __device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* top, uint64_t* bar) {
-    const uint32_t topN = S.nLeafP < kTopNodes ? S.nLeafP : kTopNodes;
+    const uint32_t topN = S.topN;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -34,22 +38,106 @@ __device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* to
     return topN;
 }
 
-// perm (optional): Morton order of the batch (qsort.cu); lane i handles query perm[i] so that a warp walks one
-// neighbourhood of the tree. A CTA owns a contiguous run of the sorted order (blocked, not grid-strided) for L1 reuse.
+// Point kernel: persistent warps with dynamic lane refill ("while-while" traversal) and batched leaf tests.
+//   * perm (optional) is the Morton order of the batch (qsort.cu); a warp claims chunks of kChunk consecutive sorted
+//     queries from a global counter, and a lane that finishes its query immediately takes the next one of the chunk, so
+//     lanes do not idle behind the slowest query of a fixed group of 32;
+//   * a lane that reaches facets (the descendants of its node are leaves) parks them as `pending` instead of running the
+//     ~170-instruction point-triangle routine on its own; the warp runs the routine when kLeafQuorum lanes are parked
+//     (or nothing else can advance), one facet per parked lane per round. Early exit is per query, as in the reference.
+constexpr int kChunk = 256;
+constexpr int kLeafQuorum = 16;
+
 __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
-                                                                uint64_t n, double eps2, uint8_t* __restrict__ out) {
+                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
     const uint32_t topN = stage_top(S, top, &bar);
-    const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + kEnvThreads - 1) / kEnvThreads * kEnvThreads;
-    const uint64_t b = (uint64_t)blockIdx.x * per, e = (b + per < n) ? b + per : n;
-    for (uint64_t i = b + threadIdx.x; i < e; i += kEnvThreads) {
-        const uint64_t src = perm ? (uint64_t)__ldg(perm + i) : i;
-        const tw::V3 p = tw::mk(__ldg(P + 3 * src), __ldg(P + 3 * src + 1), __ldg(P + 3 * src + 2));
-        uint32_t pos;
-        const bool in = twd::in_envelope(S, p, eps2, pos, top, topN);
-        out[src] = in ? 0 : 1;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const float thr = __double2float_ru(eps2);
+    const uint32_t leaf0 = S.nLeafP;
+    const uint32_t first = 1u << ((31 - __clz(leaf0)) % 3);  // start level: a multiple of three levels above the facets
+    uint64_t cb = 0, ce = 0;  // unassigned part of the warp's current chunk (warp-uniform)
+    bool more = true, active = false;
+    uint32_t pend_mask = 0, pend_c0 = 0;
+    tw::V3 p = tw::mk(0, 0, 0);
+    twd::PointF q = twd::bracket(p);
+    uint64_t src = 0;
+    uint32_t stack[64];
+    int sp = 0;
+    for (;;) {
+        const unsigned need = __ballot_sync(full, !active);
+        if (need) {
+            if (cb >= ce && more) {
+                unsigned long long c = 0;
+                if (lane == 0) c = atomicAdd(counter, 1ull);
+                c = __shfl_sync(full, c, 0);
+                cb = c * kChunk;
+                ce = (cb + kChunk < n) ? cb + kChunk : n;
+                if (cb >= n) { more = false; cb = ce = 0; }
+            }
+            if (cb < ce) {
+                const uint64_t mine = cb + __popc(need & lt);
+                if (!active && mine < ce) {
+                    src = perm ? (uint64_t)__ldg(perm + mine) : mine;  // P is already in sorted order; only the result is scattered
+                    p = tw::mk(__ldg(P + 3 * mine), __ldg(P + 3 * mine + 1), __ldg(P + 3 * mine + 2));
+                    q = twd::bracket(p);
+                    sp = 0;
+                    for (uint32_t i = 0; i < first; ++i) stack[sp++] = first + i;
+                    pend_mask = 0;
+                    active = true;
+                }
+                const uint64_t adv = cb + __popc(need);
+                cb = adv < ce ? adv : ce;
+            }
+        }
+        const unsigned act = __ballot_sync(full, active);
+        if (act == 0) {
+            if (!more) break;
+            continue;
+        }
+        const unsigned pend = __ballot_sync(full, active && pend_mask != 0);
+        if (__popc(pend) >= kLeafQuorum || pend == act) {
+            if (active && pend_mask != 0) {
+                const int c = __ffs(pend_mask) - 1;
+                pend_mask &= pend_mask - 1;
+                const uint32_t pos = pend_c0 + (uint32_t)c - leaf0;
+                if (pos < S.nF) {
+                    double s, t; tw::V3 nd; bool deg;
+                    if (twd::facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { out[src] = 0; active = false; pend_mask = 0; }
+                }
+            }
+        } else if (active && pend_mask == 0) {
+            if (sp == 0) {
+                out[src] = 1;
+                active = false;
+            } else {
+                const uint32_t node = stack[--sp];
+                if (node >= leaf0) {  // trees with fewer than three levels
+                    pend_mask = 1u; pend_c0 = node;
+                } else {
+                    float d[8];
+                    const uint32_t mask = twd::wide_step(S, q, thr, node, top, topN, d);
+                    const uint32_t c0 = 8u * node;
+                    if (c0 >= leaf0) {
+                        pend_mask = mask; pend_c0 = c0;
+                    } else {
+                        int best = -1;
+                        float bd = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (((mask >> c) & 1u) && (best < 0 || d[c] < bd)) { best = c; bd = d[c]; }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (((mask >> c) & 1u) && c != best && sp < 63) stack[sp++] = c0 + (uint32_t)c;
+                        if (best >= 0) stack[sp++] = c0 + (uint32_t)best;  // nearest subtree is popped first
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -193,7 +281,9 @@ unsigned grid_persistent(twg_ctx* c, uint64_t items, int per_block, int ctas_per
     return (unsigned)b;
 }
 
-size_t top_smem(const twg_surface* s) { return (size_t)(s->nLeafP < kTopNodes ? s->nLeafP : kTopNodes) * sizeof(NodePair); }
+uint32_t top_n(const twg_surface* s) { return s->nLeafP < kTopNodes ? s->nLeafP : kTopNodes; }
+size_t top_smem(const twg_surface* s) { return (size_t)top_n(s) * sizeof(NodePair); }
+SurfaceView view_of(const twg_surface* s) { SurfaceView v = s->view(); v.topN = top_n(s); return v; }
 
 }  // namespace
 
@@ -207,8 +297,17 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
     const uint32_t* perm = nullptr;
-    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm));
-    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), st, s->view(), dP, perm, n, eps2, dOut);
+    const double* Pq = dP;  // queries in traversal order
+    static const bool trace = getenv("TWG_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[twg] points_out_dev s=%p n=%llu st=%p lane=%d counters=%p\n", (void*)s, (unsigned long long)n, (void*)st, twg_lane_of(c, st), (void*)s->counters);
+    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm, s->sort_box, &Pq));
+    if (trace) fprintf(stderr, "[twg] sorted perm=%p Pq=%p\n", (const void*)perm, (const void*)Pq);
+    const int lane = twg_lane_of(c, st);
+    TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
+    if (trace) fprintf(stderr, "[twg] launching grid=%u smem=%zu\n", grid_persistent(c, (n + kChunk - 1) / kChunk, kEnvThreads / 32, 8), top_smem(s));
+    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, (n + kChunk - 1) / kChunk, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2,
+               dOut, s->counters + lane);
+    if (trace) fprintf(stderr, "[twg] launched\n");
     return 0;
 }
 
@@ -219,8 +318,8 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
     const uint32_t* perm = nullptr;
-    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm));
-    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), st, s->view(), dP, perm, n, dFacet, dNearest, dD2);
+    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm, s->sort_box));
+    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), st, view_of(s), dP, perm, n, dFacet, dNearest, dD2);
     return 0;
 }
 
@@ -230,7 +329,7 @@ int twg_envelope_faces_out_dev(twg_surface* s, const double* dTris, uint64_t n, 
     TWG_CHECK(c, eps2 >= 0.0 && sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need eps2 >= 0 and finite sampling_dist > 0");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, env_faces_kernel, grid_persistent(c, n, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), pick(c, stream), s->view(), dTris, n, sd, eps2, dOut);
+    TWG_LAUNCH(c, env_faces_kernel, grid_persistent(c, n, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), pick(c, stream), view_of(s), dTris, n, sd, eps2, dOut);
     return 0;
 }
 
@@ -239,7 +338,9 @@ static int points_host(twg_surface* s, int what, const double* P, uint64_t n, do
     twg_ctx* c = s->ctx;
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    const uint64_t chunk = 1ull << 22;  // 4 Mi points: 96 MiB in per slot
+    // 1 Mi points (24 MiB in) per slot by default: small enough that the first copy and the last kernel, which nothing
+    // overlaps, are a small part of a 10 M batch; large enough for the sort + traversal to run at full rate
+    static const uint64_t chunk = [] { const char* e = getenv("TWG_CHUNK_POINTS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v >= 1024 ? v : (1ull << 20); }();
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const uint64_t cmax = n < chunk ? n : chunk;
     const size_t pb = up(cmax * 24), ob = up(cmax), fb = up(cmax * 4), nb = up(cmax * 24), db = up(cmax * 8);

@@ -52,14 +52,17 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
     v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
-__global__ void __launch_bounds__(256) qkeys_kernel(const double* __restrict__ Q, uint64_t n, const unsigned long long* __restrict__ bounds,
+struct Box6 {
+    double v[6];  // lo xyz, hi xyz
+};
+__global__ void __launch_bounds__(256) qkeys_kernel(const double* __restrict__ Q, uint64_t n, const unsigned long long* __restrict__ bounds, Box6 known,
                                                     uint32_t* keys, uint32_t* vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t code = 0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const double lo = dec(bounds[c]), hi = dec(bounds[3 + c]);
+        const double lo = bounds ? dec(bounds[c]) : known.v[c], hi = bounds ? dec(bounds[3 + c]) : known.v[3 + c];
         const double ext = hi - lo;
         const double x = __ldg(Q + 3 * i + c);
         double u = (ext > 0.0 && isfinite(x)) ? (x - lo) / ext : 0.0;
@@ -70,18 +73,34 @@ __global__ void __launch_bounds__(256) qkeys_kernel(const double* __restrict__ Q
     vals[i] = (uint32_t)i;
 }
 
+// Pd[i] = P[perm[i]]: the traversal kernels then read their queries as a coalesced stream (one memory round trip per
+// refill instead of the dependent perm -> point pair), only the 1-byte / 8-byte results are scattered back.
+__global__ void __launch_bounds__(256) qgather_kernel(const double* __restrict__ P, const uint32_t* __restrict__ perm, uint64_t n, double* __restrict__ Pd) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t s = (uint64_t)__ldg(perm + i);
+    const double x = __ldg(P + 3 * s), y = __ldg(P + 3 * s + 1), z = __ldg(P + 3 * s + 2);
+    Pd[3 * i] = x; Pd[3 * i + 1] = y; Pd[3 * i + 2] = z;
+}
+
 }  // namespace
 
 // perm_out[i] = index (in the caller's order) of the i-th point along the Morton curve. `lane` selects one of the
 // TWG_NUM_STREAMS + 1 sort scratch buffers of the context (one per staging stream + one for external streams).
-int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out) {
+// known_box (optional, host: lo xyz, hi xyz): quantise over this box (points outside are clamped to its faces)
+// instead of reducing the batch's own bounding box first -- the surface's box is what matters to both traversals.
+int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box,
+                    const double** sorted_out) {
     TWG_CHECK(c, n < 0xffffffffull, TWG_ERR_INVALID_ARG, "at most 2^32-2 queries per call");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     size_t tmp_bytes = 0;
     TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                                 (int)n, 0, 30, st));
+    static const bool trace = getenv("TWG_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[twg] sort lane=%d n=%llu tmp=%zu have=%zu\n", lane, (unsigned long long)n, tmp_bytes, c->dsort_bytes[lane]);
     const size_t kb = up(n * 4);
-    const size_t need = 256 + 4 * kb + up(tmp_bytes);
+    const size_t pb = sorted_out ? up(n * 24) : 0;
+    const size_t need = 256 + 4 * kb + up(tmp_bytes) + pb;
     if (c->dsort_bytes[lane] < need) {
         if (c->dsort[lane]) {
             TWG_CUDA(c, cudaStreamSynchronize(st));
@@ -98,13 +117,22 @@ int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uin
     uint32_t *keys = (uint32_t*)(base + 256), *keys2 = (uint32_t*)(base + 256 + kb), *vals = (uint32_t*)(base + 256 + 2 * kb),
              *vals2 = (uint32_t*)(base + 256 + 3 * kb);
     void* tmp = base + 256 + 4 * kb;
-    TWG_LAUNCH(c, qinit_kernel, 1, 32, 0, st, bounds);
-    uint64_t g = (3 * n + 255) / 256;
-    if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
-    TWG_LAUNCH(c, qbounds_kernel, (unsigned)g, 256, 0, st, dP, n, bounds);
-    TWG_LAUNCH(c, qkeys_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, n, bounds, keys, vals);
+    Box6 known;
+    for (int k = 0; k < 6; ++k) known.v[k] = known_box ? known_box[k] : 0.0;
+    if (!known_box) {
+        TWG_LAUNCH(c, qinit_kernel, 1, 32, 0, st, bounds);
+        uint64_t g = (3 * n + 255) / 256;
+        if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
+        TWG_LAUNCH(c, qbounds_kernel, (unsigned)g, 256, 0, st, dP, n, bounds);
+    }
+    TWG_LAUNCH(c, qkeys_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, keys, vals);
     TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 30, st));
     c->launches += 5;  // cub: histogram + exclusive-sum + one onesweep pass per 8 key bits (library kernels)
     *perm_out = vals2;
+    if (sorted_out) {
+        double* Pd = (double*)(base + 256 + 4 * kb + up(tmp_bytes));
+        TWG_LAUNCH(c, qgather_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, vals2, n, Pd);
+        *sorted_out = Pd;
+    }
     return 0;
 }

@@ -152,6 +152,7 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
     B_CUDA(cudaMalloc(&s->tris, sizeof(tw::TriRec) * (size_t)nF));
     B_CUDA(cudaMalloc(&s->triV, sizeof(double) * 9 * (size_t)nF));
     B_CUDA(cudaMalloc(&bounds, 6 * sizeof(unsigned long long)));
+    B_CUDA(cudaMalloc(&s->counters, (TWG_NUM_STREAMS + 1) * sizeof(unsigned long long)));
     B_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)nF));
     B_CUDA(cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)nF));
     B_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)nF));
@@ -178,7 +179,17 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
         c->launches++;
     }
     B_CUDA(cudaGetLastError());
-    B_CUDA(cudaStreamSynchronize(st));
+    {
+        unsigned long long hb[6];
+        B_CUDA(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
+        B_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 6; ++k) s->bbox[k] = dec(hb[k]);
+        for (int k = 0; k < 3; ++k) {
+            const double m = 0.05 * (s->bbox[3 + k] - s->bbox[k]);
+            s->sort_box[k] = s->bbox[k] - m;
+            s->sort_box[3 + k] = s->bbox[3 + k] + m;
+        }
+    }
 #undef B_CUDA
     cudaFree(bounds); cudaFree(keys); cudaFree(keys2); cudaFree(vals); cudaFree(vals2); cudaFree(tmp);
     *out = s;
@@ -195,6 +206,7 @@ void twg_surface_destroy(twg_surface* s) {
     cudaFree(s->pairs);
     cudaFree(s->tris);
     cudaFree(s->triV);
+    cudaFree(s->counters);
     delete s;
 }
 

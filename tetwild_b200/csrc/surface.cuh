@@ -24,6 +24,7 @@ struct SurfaceView {
     const double* triV;
     uint32_t nF;
     uint32_t nLeafP;  // power of two >= max(nF, 2)
+    uint32_t topN;    // pair records [0, topN) are staged in shared memory by the query kernels
 };
 
 struct twg_surface {
@@ -33,7 +34,10 @@ struct twg_surface {
     tw::TriRec* tris = nullptr;
     double* triV = nullptr;
     bool no_sort = false;  // TWG_ENVELOPE_SORT=0: traverse batches in the caller's order (profiling aid)
-    SurfaceView view() const { return SurfaceView{pairs, tris, triV, nF, nLeafP}; }
+    unsigned long long* counters = nullptr;  // one work counter per sort lane (persistent point kernel)
+    double bbox[6] = {0, 0, 0, 0, 0, 0};     // lo xyz, hi xyz of the surface
+    double sort_box[6] = {0, 0, 0, 0, 0, 0}; // bbox grown by 5 %: Morton quantisation box of query batches (qsort.cu)
+    SurfaceView view() const { return SurfaceView{pairs, tris, triV, nF, nLeafP, 0}; }
 };
 
 #if defined(__CUDACC__)
@@ -101,78 +105,65 @@ __device__ __forceinline__ float box_d2_lb(const PointF& q, float lx, float ly, 
 }
 
 // Is some facet within sqrt(eps2) of p?  (facet_in_envelope_recursive, mesh_AABB.cpp:482-548: stop at the first
-// facet with d2 <= eps2, never enter a box farther than eps.)
-//
-// 8-wide traversal of the implicit binary heap: the boxes of the eight descendants 8i .. 8i+7 of node i (three levels
-// down) are the four CONSECUTIVE pair records 4i .. 4i+3 = one 192-byte run, fetched with twelve independent 128-bit
-// loads. A query near the surface therefore makes ceil(depth / 3) dependent memory round trips instead of depth
-// (6 instead of 18 for 200k facets; the first three come from the shared-memory copy of the top of the tree), which
-// is what bounds a traversal whose arithmetic per node is ~100 FP32 instructions. top/topN: pair records [0, topN)
-// staged in shared memory.
+// facet with d2 <= eps2, never enter a box farther than eps.)  Binary descent, one query per lane; used by the
+// face kernel, whose lanes each walk their own run of samples. top/topN: pair records [0, topN) staged in shared memory.
 __device__ __forceinline__ bool in_envelope(const SurfaceView& S, tw::V3 p, double eps2, uint32_t& hit_pos, const NodePair* top, uint32_t topN) {
     const float thr = __double2float_ru(eps2);
     const PointF q = bracket(p);
-    const uint32_t leaf0 = S.nLeafP;
-    uint32_t stack[64];
+    uint32_t stack[32];
     int sp = 0;
-    // the heap has log2(leaf0) levels below the root; start at the level that leaves a multiple of three below it
-    {
-        const int k = 31 - __clz(leaf0);
-        const int r = k % 3;
-        const uint32_t first = 1u << r;
-        for (uint32_t i = 0; i < first; ++i) stack[sp++] = first + i;  // <= 4 subtrees, entered without a box test
-    }
-    while (sp > 0) {
-        const uint32_t node = stack[--sp];
-        if (node >= leaf0) {  // only when the whole tree has fewer than three levels
-            const uint32_t pos = node - leaf0;
-            if (pos < S.nF) {
-                double s, t; tw::V3 nd; bool deg;
-                if (facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { hit_pos = pos; return true; }
+    uint32_t node = 1;
+    const uint32_t leaf0 = S.nLeafP;
+    for (;;) {
+        NodePair np = (node < topN) ? top[node] : load_pair(S.pairs + node);
+        const float dl = box_d2_lb(q, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
+        const float dr = box_d2_lb(q, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
+        const bool hl = dl <= thr, hr = dr <= thr;
+        const uint32_t cl = 2u * node;
+        if (cl >= leaf0) {
+            const bool lfirst = !(hr && dr < dl);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const bool left = (k == 0) ? lfirst : !lfirst;
+                const uint32_t pos = (left ? cl : cl + 1u) - leaf0;
+                if ((left ? hl : hr) && pos < S.nF) {
+                    double s, t; tw::V3 nd; bool deg;
+                    const double d2 = facet_d2(S, pos, p, s, t, nd, deg);
+                    if (d2 <= eps2) { hit_pos = pos; return true; }
+                }
+            }
+        } else if (hl || hr) {
+            if (hl && hr) {
+                const bool lnear = dl <= dr;
+                stack[sp++] = lnear ? cl + 1u : cl;
+                node = lnear ? cl : cl + 1u;
+            } else {
+                node = hl ? cl : cl + 1u;
             }
             continue;
         }
-        const uint32_t c0 = 8u * node;       // first descendant three levels down
-        const uint32_t pr = 4u * node;       // its pair record
-        float d[8];
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const NodePair np = (pr + 3u < topN) ? top[pr + h] : load_pair(S.pairs + pr + h);
-            d[2 * h] = box_d2_lb(q, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
-            d[2 * h + 1] = box_d2_lb(q, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
-        }
-        if (c0 >= leaf0) {
-            // descendants are facets: test the admitted ones, nearest box first
-            uint32_t mask = 0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) mask |= (d[c] <= thr) ? (1u << c) : 0u;
-            while (mask) {
-                int best = -1;
-                float bd = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    if (((mask >> c) & 1u) && (best < 0 || d[c] < bd)) { best = c; bd = d[c]; }
-                mask &= ~(1u << best);
-                const uint32_t pos = c0 + (uint32_t)best - leaf0;
-                if (pos < S.nF) {
-                    double s, t; tw::V3 nd; bool deg;
-                    if (facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { hit_pos = pos; return true; }
-                }
-            }
-        } else {
-            // push the admitted subtrees, the nearest one last so that it is popped first
-            int best = -1;
-            float bd = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (d[c] <= thr && (best < 0 || d[c] < bd)) { best = c; bd = d[c]; }
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-                if (d[c] <= thr && c != best && sp < 63) stack[sp++] = c0 + (uint32_t)c;
-            if (best >= 0) stack[sp++] = c0 + (uint32_t)best;
-        }
+        if (sp == 0) return false;
+        node = stack[--sp];
     }
-    return false;
+}
+
+// One step of the 8-wide traversal used by the point kernel: the boxes of the eight descendants 8i .. 8i+7 of heap
+// node i (three levels down) are the four CONSECUTIVE pair records 4i .. 4i+3 = one 192-byte run, fetched with twelve
+// independent 128-bit loads. A query near the surface makes ceil(depth / 3) dependent memory round trips instead of
+// depth (6 instead of 18 for 200k facets, the first three from the shared-memory copy of the top of the tree).
+// Returns the bit mask of admitted descendants and their lower-bound distances.
+__device__ __forceinline__ uint32_t wide_step(const SurfaceView& S, const PointF& q, float thr, uint32_t node, const NodePair* top, uint32_t topN, float d[8]) {
+    const uint32_t pr = 4u * node;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const NodePair np = (pr + 3u < topN) ? top[pr + h] : load_pair(S.pairs + pr + h);
+        d[2 * h] = box_d2_lb(q, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
+        d[2 * h + 1] = box_d2_lb(q, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
+    }
+    uint32_t mask = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mask |= (d[c] <= thr) ? (1u << c) : 0u;
+    return mask;
 }
 
 struct Nearest {

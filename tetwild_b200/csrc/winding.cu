@@ -525,6 +525,7 @@ struct twg_winding {
     uint32_t nBlkP = 1, nF = 0;
     uint64_t n_nodes = 0, n_caps = 0;
     uint32_t leaf = 64;  // triangles per leaf block (TWG_WINDING_LEAF)
+    double sort_box[6] = {0, 0, 0, 0, 0, 0};  // surface bbox grown by 10 %: Morton quantisation box of query batches
     bool sort_queries = true;
     WView view() const { return WView{nodes, caps, tris, nBlkP, nF}; }
 };
@@ -553,6 +554,11 @@ int twg_winding_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t*
     if (nF == 0) { *out = w; return 0; }
     HostTree T;
     build_host_tree(V, nV, F, nF, w->leaf, T);
+    for (int k = 0; k < 3; ++k) {  // root box
+        const double lo = T.nodes[1].lo[k], hi = T.nodes[1].hi[k], m = 0.1 * (hi - lo);
+        w->sort_box[k] = lo - m;
+        w->sort_box[3 + k] = hi + m;
+    }
     w->nBlkP = T.nBlkP;
     w->n_nodes = T.nodes.size();
     w->n_caps = T.caps.size() / 4;
@@ -590,7 +596,7 @@ int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* 
         return 0;
     }
     const uint32_t* perm = nullptr;
-    if (w->sort_queries && nC > 32) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dC, nC, &perm));
+    if (w->sort_queries && nC > 32) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dC, nC, &perm, w->sort_box));
     const uint64_t ngroups = (nC + 31) / 32;
     unsigned grid = (unsigned)std::min<uint64_t>((ngroups + kWarps - 1) / kWarps, (uint64_t)c->sm_count * 32);
     TWG_LAUNCH(c, winding_kernel, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
