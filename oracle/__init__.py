@@ -75,7 +75,12 @@ def lib():
 
 
 def max_threads():
-    return int(lib().ora_max_threads())
+    """Host threads available to this process. Not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1, and every
+    oracle entry point passes its thread count explicitly (num_threads clause), which overrides that variable."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 # ---------------------------------------------------------------------------------------------- predicates
