@@ -137,14 +137,17 @@ __device__ __forceinline__ double warp_sum(double v) {
 template <bool ENERGY_ONLY>
 __global__ void __launch_bounds__(256) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
                                                          const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
-                                                         const int32_t* __restrict__ center, uint64_t nG, double* __restrict__ E,
-                                                         double* __restrict__ J3, double* __restrict__ H9, uint8_t* __restrict__ ok) {
+                                                         const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
+                                                         double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
+                                                         uint8_t* __restrict__ ok) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t g = warp; g < nG; g += nwarps) {
-        const uint64_t b = __ldg(off + g), e = __ldg(off + g + 1);
-        const int32_t c = ENERGY_ONLY ? 0 : __ldg(center + g);
+        // vids != NULL: group g is the one-ring of vertex vids[g] in a vertex -> tets CSR (conn_tets of the resident mesh)
+        const uint64_t row = vids ? (uint64_t)__ldg(vids + g) : g;
+        const uint64_t b = __ldg(off + row), e = __ldg(off + row + 1);
+        const int32_t c = vids ? (int32_t)row : (ENERGY_ONLY ? 0 : __ldg(center + g));
         double acc[13];
 #pragma unroll
         for (int k = 0; k < 13; ++k) acc[k] = 0.0;
@@ -273,7 +276,19 @@ int twg_amips_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int3
     if (nG == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
-               dCenter, nG, dE, dJ3, dH9, dOk);
+               dCenter, (const int32_t*)nullptr, nG, dE, dJ3, dH9, dOk);
+    return 0;
+}
+
+// one-rings named by their centre vertex: members of ring g are adj_tets[adj_off[v] .. adj_off[v+1]) with v = dVids[g]
+int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, const int32_t* dTets, const int32_t* dAdjTets, const uint64_t* dAdjOff,
+                                  const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk, void* stream) {
+    TWG_CHECK(c, c && dV && dTets && dAdjTets && dAdjOff && dVids && dE && dJ3 && dH9, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
+    if (nG == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dAdjTets, dAdjOff,
+               (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk);
     return 0;
 }
 
@@ -285,7 +300,7 @@ int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const i
     if (nG == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
-               (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr);
+               (const int32_t*)nullptr, (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr);
     return 0;
 }
 

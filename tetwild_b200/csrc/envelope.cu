@@ -38,30 +38,51 @@ __device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* to
     return topN;
 }
 
-// Point kernel: persistent warps with dynamic lane refill ("while-while" traversal) and batched leaf tests.
-//   * perm (optional) is the Morton order of the batch (qsort.cu); a warp claims chunks of kChunk consecutive sorted
-//     queries from a global counter, and a lane that finishes its query immediately takes the next one of the chunk, so
-//     lanes do not idle behind the slowest query of a fixed group of 32;
-//   * a lane that reaches facets (the descendants of its node are leaves) parks them as `pending` instead of running the
-//     ~170-instruction point-triangle routine on its own; the warp runs the routine when kLeafQuorum lanes are parked
-//     (or nothing else can advance), one facet per parked lane per round. Early exit is per query, as in the reference.
-constexpr int kChunk = 256;
+// Point kernel: persistent warps, WARP-COOPERATIVE descent of the upper tree + per-lane finish, dynamic lane refill and
+// batched leaf tests.
+//   * perm (optional) is the Morton order of the batch (qsort.cu). A warp claims GROUPS of `group` consecutive sorted
+//     queries from a global counter. For each group the 32 lanes together walk the upper levels ONCE: they reduce the
+//     group's bounding box, dilate it by eps (outward-rounded floats) and refine a FRONTIER of heap nodes three levels
+//     at a time -- lane j tests candidate box j against the dilated group box, survivors are compacted with a ballot into
+//     a per-warp shared-memory list (node id + its float box) -- until the frontier's children are facets or it would
+//     exceed kFrontMax nodes. Box-vs-group-box overlap is a superset of "some query of the group is within eps of the
+//     box", so no subtree that any query needs is lost; a group that straddles a jump of the Morton curve merely keeps a
+//     shallower frontier (worst case: the root level = the old per-lane traversal).
+//   * a lane then starts its query from the frontier (one conservative FP32 box test per frontier node, warp-uniform loop
+//     over shared memory), nearest node first, and continues with private 8-wide steps (surface.cuh); typically one or
+//     two steps remain instead of ceil(depth/3).
+//   * a lane that finishes its query immediately takes the next one of the group; the frontier is only read when a query
+//     starts, so the warp moves on to the next group while slower lanes are still finishing;
+//   * a lane that reaches facets parks them as `pending` instead of running the ~170-instruction point-triangle routine
+//     on its own; the warp runs the routine when kLeafQuorum lanes are parked (or nothing else can advance), one facet
+//     per parked lane per round. Early exit is per query, as in the reference (mesh_AABB.cpp:489).
+constexpr int kFrontMax = 32;
 constexpr int kLeafQuorum = 16;
+struct Front {
+    uint32_t node[kFrontMax];
+    float box[kFrontMax][6];
+};
 
 __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
-                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter) {
+                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
+    __shared__ Front fronts[kEnvThreads / 32][2];
     const uint32_t topN = stage_top(S, top, &bar);
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const float thr = __double2float_ru(eps2);
+    const float epsf = __fsqrt_ru(thr);
     const uint32_t leaf0 = S.nLeafP;
-    const uint32_t first = 1u << ((31 - __clz(leaf0)) % 3);  // start level: a multiple of three levels above the facets
-    uint64_t cb = 0, ce = 0;  // unassigned part of the warp's current chunk (warp-uniform)
+    const int L = 31 - __clz(leaf0);
+    const uint32_t first = 1u << (L % 3);  // start level: a multiple of three levels above the facets
+    const float inf = __int_as_float(0x7f800000);
+    uint64_t cb = 0, ce = 0;  // unassigned part of the warp's current group (warp-uniform)
     bool more = true, active = false;
+    const Front* fr = &fronts[wib][0];  // frontier of the current group (warp-uniform)
+    int fcount = 0;
     uint32_t pend_mask = 0, pend_c0 = 0;
     tw::V3 p = tw::mk(0, 0, 0);
     twd::PointF q = twd::bracket(p);
@@ -75,9 +96,78 @@ __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, 
                 unsigned long long c = 0;
                 if (lane == 0) c = atomicAdd(counter, 1ull);
                 c = __shfl_sync(full, c, 0);
-                cb = c * kChunk;
-                ce = (cb + kChunk < n) ? cb + kChunk : n;
+                cb = c * (uint64_t)group;
+                ce = (cb + group < n) ? cb + group : n;
                 if (cb >= n) { more = false; cb = ce = 0; }
+                if (cb < ce) {
+                    // ---- group bounding box, dilated by eps (outward-rounded floats)
+                    float lo[3] = {inf, inf, inf}, hi[3] = {-inf, -inf, -inf};
+                    for (uint64_t j = cb + lane; j < ce; j += 32) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const double x = __ldg(P + 3 * j + k);
+                            lo[k] = fminf(lo[k], __double2float_rd(x));
+                            hi[k] = fmaxf(hi[k], __double2float_ru(x));
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            lo[k] = fminf(lo[k], __shfl_xor_sync(full, lo[k], o));
+                            hi[k] = fmaxf(hi[k], __shfl_xor_sync(full, hi[k], o));
+                        }
+                        lo[k] = __fsub_rd(lo[k], epsf);
+                        hi[k] = __fadd_ru(hi[k], epsf);
+                    }
+                    // ---- cooperative refinement of the frontier; the buffer not referenced by `fr` is free: lanes still
+                    // working on the previous group never look at a frontier again
+                    Front* A = const_cast<Front*>(fr == &fronts[wib][0] ? &fronts[wib][1] : &fronts[wib][0]);
+                    Front* B = const_cast<Front*>(fr);
+                    __syncwarp();
+                    if ((uint32_t)lane < first) {
+                        A->node[lane] = first + lane;
+                        A->box[lane][0] = A->box[lane][1] = A->box[lane][2] = -inf;  // root-level boxes are not stored: always admitted
+                        A->box[lane][3] = A->box[lane][4] = A->box[lane][5] = inf;
+                    }
+                    __syncwarp();
+                    int count = (int)first;
+                    for (int d = L % 3; d + 3 <= L - 3 && count > 0; d += 3) {
+                        const int total = 8 * count;
+                        int ncount = 0;
+                        bool overflow = false;
+                        for (int base = 0; base < total; base += 32) {
+                            const int idx = base + lane;
+                            bool ok = false;
+                            uint32_t child = 0;
+                            float b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+                            if (idx < total) {
+                                child = 8u * A->node[idx >> 3] + (uint32_t)(idx & 7);
+                                const float* rec = reinterpret_cast<const float*>(S.pairs + (child >> 1)) + 6 * (child & 1u);
+                                const float2 u = __ldg(reinterpret_cast<const float2*>(rec));
+                                const float2 v = __ldg(reinterpret_cast<const float2*>(rec) + 1);
+                                const float2 w = __ldg(reinterpret_cast<const float2*>(rec) + 2);
+                                b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y; b4 = w.x; b5 = w.y;
+                                ok = b0 <= hi[0] && b3 >= lo[0] && b1 <= hi[1] && b4 >= lo[1] && b2 <= hi[2] && b5 >= lo[2];
+                            }
+                            const unsigned m = __ballot_sync(full, ok);
+                            if (ncount + __popc(m) > kFrontMax) { overflow = true; break; }
+                            if (ok) {
+                                const int pos = ncount + __popc(m & lt);
+                                B->node[pos] = child;
+                                B->box[pos][0] = b0; B->box[pos][1] = b1; B->box[pos][2] = b2;
+                                B->box[pos][3] = b3; B->box[pos][4] = b4; B->box[pos][5] = b5;
+                            }
+                            ncount += __popc(m);
+                        }
+                        __syncwarp();
+                        if (overflow) break;
+                        Front* t = A; A = B; B = t;
+                        count = ncount;
+                    }
+                    fr = A;
+                    fcount = count;
+                }
             }
             if (cb < ce) {
                 const uint64_t mine = cb + __popc(need & lt);
@@ -86,7 +176,16 @@ __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, 
                     p = tw::mk(__ldg(P + 3 * mine), __ldg(P + 3 * mine + 1), __ldg(P + 3 * mine + 2));
                     q = twd::bracket(p);
                     sp = 0;
-                    for (uint32_t i = 0; i < first; ++i) stack[sp++] = first + i;
+                    int best = -1;
+                    float bd = 0.f;
+                    for (int i = 0; i < fcount; ++i) {
+                        const float d = twd::box_d2_lb(q, fr->box[i][0], fr->box[i][1], fr->box[i][2], fr->box[i][3], fr->box[i][4], fr->box[i][5]);
+                        if (d <= thr) {
+                            if (best < 0 || d < bd) { best = sp; bd = d; }
+                            stack[sp++] = fr->node[i];
+                        }
+                    }
+                    if (best >= 0 && best != sp - 1) { const uint32_t t = stack[best]; stack[best] = stack[sp - 1]; stack[sp - 1] = t; }  // nearest first
                     pend_mask = 0;
                     active = true;
                 }
@@ -147,14 +246,24 @@ __global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, con
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
     const uint32_t topN = stage_top(S, top, &bar);
-    const uint64_t per = ((n + gridDim.x - 1) / gridDim.x + kEnvThreads - 1) / kEnvThreads * kEnvThreads;
-    const uint64_t b0 = (uint64_t)blockIdx.x * per, e0 = (b0 + per < n) ? b0 + per : n;
-    for (uint64_t j = b0 + threadIdx.x; j < e0; j += kEnvThreads) {
+    // every thread walks a RUN of consecutive Morton-sorted queries and starts each search from the facet nearest to
+    // its previous query (nearest_facet_with_hint, mesh_AABB.h:162-176 / get_nearest_facet_hint :381-416 play the same
+    // role): the initial bound is already within a facet or two of the answer, so far queries no longer open every
+    // box on the way down. The result is the minimum over all facets either way.
+    const uint64_t run = (n + (uint64_t)gridDim.x * kEnvThreads - 1) / ((uint64_t)gridDim.x * kEnvThreads);
+    const uint64_t b0 = ((uint64_t)blockIdx.x * kEnvThreads + threadIdx.x) * run, e0 = (b0 + run < n) ? b0 + run : n;
+    uint32_t hint = TWG_NO_FACET;
+    for (uint64_t j = b0; j < e0; ++j) {
         const uint64_t i = perm ? (uint64_t)__ldg(perm + j) : j;
         const tw::V3 p = tw::mk(__ldg(P + 3 * i), __ldg(P + 3 * i + 1), __ldg(P + 3 * i + 2));
         twd::Nearest b;
         b.d2 = DBL_MAX; b.s = b.t = 0.0; b.pos = 0; b.deg = false; b.pt_deg = p;
+        if (hint != TWG_NO_FACET) {
+            b.pos = hint;
+            b.d2 = twd::facet_d2(S, hint, p, b.s, b.t, b.pt_deg, b.deg);
+        }
         twd::nearest_facet(S, p, b, top, topN);
+        hint = b.pos;
         if (d2out) d2out[i] = b.d2;
         if (facet || nearest) {
             const tw::TriRec r = twd::load_tri(S.tris + b.pos);
@@ -304,9 +413,10 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     if (trace) fprintf(stderr, "[twg] sorted perm=%p Pq=%p\n", (const void*)perm, (const void*)Pq);
     const int lane = twg_lane_of(c, st);
     TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
-    if (trace) fprintf(stderr, "[twg] launching grid=%u smem=%zu\n", grid_persistent(c, (n + kChunk - 1) / kChunk, kEnvThreads / 32, 8), top_smem(s));
-    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, (n + kChunk - 1) / kChunk, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2,
-               dOut, s->counters + lane);
+    // queries per cooperative group (tuning aid; 64 measured best on C2)
+    static const int group = [] { const char* e = getenv("TWG_ENV_GROUP"); int v = e ? atoi(e) : 64; return v < 32 ? 32 : (v > 4096 ? 4096 : v); }();
+    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2,
+               dOut, s->counters + lane, group);
     if (trace) fprintf(stderr, "[twg] launched\n");
     return 0;
 }
