@@ -110,6 +110,43 @@ int twg_amips_ring_energy(twg_ctx* ctx, const double* Vxyz, uint32_t nV, const i
 int twg_amips_ring_energy_dev(twg_ctx* ctx, const double* dVxyz, uint32_t nV, const int32_t* dTets4, uint64_t nT,
                               const int32_t* dTids, const uint64_t* dGroupOff, uint64_t nGroups, double* dE, void* stream);
 
+/* ---- resident tet mesh (S3 callers: whole-mesh passes and one-ring batches without re-shipping the mesh) ---------- */
+/* Device mirror of the scheduler's `tet_vertices[].posf`, `tets`, `t_is_removed` and `tet_vertices[].conn_tets`
+ * (src/tetwild/LocalOperations.h:35-45). Created once after the front end (MeshRefinement.cpp:208), then kept in step
+ * with accepted operations through the two scatter calls; AMIPS batches then move only ids in and results out.
+ * A removed tet (t_is_removed[t]) is a tet whose first index is negative. Slots only grow, like the host vectors. */
+typedef struct twg_mesh twg_mesh;
+int twg_mesh_create(twg_ctx* ctx, const double* Vxyz, uint32_t nV, const int32_t* tets4, uint64_t nT, twg_mesh** out);
+void twg_mesh_destroy(twg_mesh* m);
+uint32_t twg_mesh_num_vertices(const twg_mesh* m);
+uint64_t twg_mesh_num_tets(const twg_mesh* m);
+const double* twg_mesh_vertices_dev(const twg_mesh* m);  /* device pointers, valid until the next resize */
+const int32_t* twg_mesh_tets_dev(const twg_mesh* m);
+int twg_mesh_resize(twg_mesh* m, uint32_t nV, uint64_t nT);  /* new vertex slots are 0, new tet slots are removed */
+int twg_mesh_set_vertices(twg_mesh* m, const int32_t* v_ids, const double* xyz, uint64_t n);    /* posf[v_ids[i]] = xyz[i] */
+int twg_mesh_set_tets(twg_mesh* m, const int32_t* t_ids, const int32_t* tets4, uint64_t n);     /* tets[t_ids[i]] = tets4[i] */
+int twg_mesh_get_vertices(twg_mesh* m, double* xyz_out /* nV*3 */);
+/* conn_tets rebuilt on the device (vertex -> incident live tets, ascending tet id); get_rings copies it back:
+ * off_out[nV+1], tets_out[off_out[nV]] (tets_out may be NULL to query sizes) */
+int twg_mesh_build_rings(twg_mesh* m);
+int twg_mesh_get_rings(twg_mesh* m, uint64_t* off_out, int32_t* tets_out);
+/* a4 over the resident mesh: calTetQuality_AMIPS (LocalOperations.cpp:862-884) of tets t_ids[0..n) (t_ids NULL: all
+ * nT slots; removed tets give MAX_ENERGY). The whole-mesh callers: VertexSmoother.cpp:216-241, MeshRefinement.cpp:51 */
+int twg_mesh_quality(twg_mesh* m, const int32_t* t_ids, uint64_t n, double* slim_energy);
+int twg_mesh_quality_dev(twg_mesh* m, const int32_t* dTids, uint64_t n, double* dSlim, void* stream);
+/* calTetQuality_AD (LocalOperations.cpp:783-860): min / max dihedral angle per tet (0 and pi for degenerate tets),
+ * what LocalOperations::outputInfo (:348-354) and getFilteredAngles collect over all live tets */
+int twg_mesh_dihedral(twg_mesh* m, const int32_t* t_ids, uint64_t n, double* min_d_angle, double* max_d_angle);
+int twg_mesh_dihedral_dev(twg_mesh* m, const int32_t* dTids, uint64_t n, double* dMin, double* dMax, void* stream);
+/* a5 (NewtonsUpdate, VertexSmoother.cpp:627-702) for the one-rings of vertices v_ids[0..n): members are conn_tets[v] */
+int twg_mesh_vertex_ring_ejh(twg_mesh* m, const int32_t* v_ids, uint64_t n, double* E, double* J3, double* H9, uint8_t* ok);
+int twg_mesh_vertex_ring_ejh_dev(twg_mesh* m, const int32_t* dVids, uint64_t n, double* dE, double* dJ3, double* dH9, uint8_t* dOk,
+                                 void* stream);
+/* a5 / a6 with explicit member lists (CSR over t_ids) against the resident mesh */
+int twg_mesh_ring_ejh(twg_mesh* m, const int32_t* t_ids, const uint64_t* group_off, const int32_t* center, uint64_t nGroups,
+                      double* E, double* J3, double* H9, uint8_t* ok);
+int twg_mesh_ring_energy(twg_mesh* m, const int32_t* t_ids, const uint64_t* group_off, uint64_t nGroups, double* E);
+
 /* ---- S4: generalized winding number ------------------------------------------------------------------------------ */
 /* F may contain repeated faces (InoutFiltering.cpp:99-100). */
 int twg_winding_create(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out);

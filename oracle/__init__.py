@@ -174,6 +174,15 @@ def amips_ring_energy(V, tets, group_off, t_ids=None, threads=1):
     return E
 
 
+def tet_dihedral(V, tets, threads=1):
+    """calTetQuality_AD (LocalOperations.cpp:783-860): (min_d_angle, max_d_angle) per tet"""
+    V, tets = _f64(V), _i32(tets)
+    n = tets.shape[0]
+    lo, hi = np.empty(n), np.empty(n)
+    lib().ora_tet_dihedral(_p(V, _dp), _p(tets, _i32p), C.c_uint64(n), _p(lo, _dp), _p(hi, _dp), C.c_int(threads))
+    return lo, hi
+
+
 # ---------------------------------------------------------------------------------------------- envelope
 def point_triangle_sqdist(p, v0, v1, v2):
     a = [_f64(x) for x in (p, v0, v1, v2)]

@@ -261,3 +261,70 @@ void ora_amips_ring_energy(const double *V, const int32_t *tets, const int32_t *
         E[g] = s;
     }
 }
+
+/* calTetQuality_AD: LocalOperations.cpp:783-860 (min / max dihedral angle of a tet).
+ * Plane_3f(p,q,r) and Plane_3f::projection are CGAL constructions on Cartesian<double> (CGALTypes.h; CGAL is a system
+ * package, not vendored -> restated from its published kernel_ftC3.h: plane_from_pointsC3, projection_planeC3,
+ * squared_distanceC3). PARITY UNPINNED for those two constructions; everything else follows the reference text.
+ * Built with -ffp-contract=off: plain IEEE double like the reference's x86-64 Release build. */
+static int tet_dihedral(const double *x, double *amin, double *amax) {
+    double nv[4][3], len[4];
+    for (int i = 0; i < 4; ++i) {
+        const double *P = x + 3 * ((i + 1) % 4), *Q = x + 3 * ((i + 2) % 4), *R = x + 3 * ((i + 3) % 4), *A = x + 3 * i;
+        /* plane_from_pointsC3 */
+        const double rpx = P[0] - R[0], rpy = P[1] - R[1], rpz = P[2] - R[2];
+        const double rqx = Q[0] - R[0], rqy = Q[1] - R[1], rqz = Q[2] - R[2];
+        const double pa = rpy * rqz - rqy * rpz, pb = rpz * rqx - rqz * rpx, pc = rpx * rqy - rqx * rpy;
+        const double pd = -pa * R[0] - pb * R[1] - pc * R[2];
+        if (pa == 0 && pb == 0 && pc == 0) return 0; /* pln.is_degenerate() :790 */
+        /* projection_planeC3 */
+        const double num = pa * A[0] + pb * A[1] + pc * A[2] + pd;
+        const double den = pa * pa + pb * pb + pc * pc;
+        const double lambda = num / den;
+        const double t[3] = {A[0] - lambda * pa, A[1] - lambda * pb, A[2] - lambda * pc};
+        if (t[0] == A[0] && t[1] == A[1] && t[2] == A[2]) return 0; /* :796 */
+        for (int k = 0; k < 3; ++k) nv[i][k] = A[k] - t[k];          /* :801 */
+        const double h = nv[i][0] * nv[i][0] + nv[i][1] * nv[i][1] + nv[i][2] * nv[i][2]; /* :802 */
+        double m = fabs(nv[i][0]);
+        if (fabs(nv[i][1]) > m) m = fabs(nv[i][1]);
+        if (fabs(nv[i][2]) > m) m = fabs(nv[i][2]);
+        if (m == 0 || h == 0) return 0; /* :820 */
+        if (m < 1e-5) {                 /* :825-828 */
+            for (int k = 0; k < 3; ++k) nv[i][k] = nv[i][k] / m;
+            len[i] = sqrt(h / (m * m));
+        } else {
+            len[i] = sqrt(h);
+        }
+    }
+    static const int ea[6] = {0, 1, 0, 2, 0, 3}, eb[6] = {1, 2, 2, 3, 3, 1}; /* opp_edges :834-838 */
+    double ang[6];
+    for (int k = 0; k < 6; ++k) {
+        const double *a = nv[ea[k]], *b = nv[eb[k]];
+        const double c = ((-a[0]) * b[0] + (-a[1]) * b[1] + (-a[2]) * b[2]) / (len[ea[k]] * len[eb[k]]); /* :843-844 */
+        ang[k] = c > 1 ? 0.0 : (c < -1 ? M_PI : acos(c));
+    }
+    double lo = ang[0], hi = ang[0]; /* std::minmax_element :854: first smallest, last largest */
+    for (int k = 1; k < 6; ++k) {
+        if (ang[k] < lo) lo = ang[k];
+        if (!(ang[k] < hi)) hi = ang[k];
+    }
+    *amin = lo;
+    *amax = hi;
+    return 1;
+}
+
+void ora_tet_dihedral(const double *V, const int32_t *tets, uint64_t nT, double *dmin, double *dmax, int threads) {
+    (void)threads;
+#pragma omp parallel for schedule(static) num_threads(threads > 0 ? threads : 1)
+    for (int64_t i = 0; i < (int64_t)nT; ++i) {
+        double T[12], lo = 0.0, hi = M_PI; /* degenerate answers :791-792 */
+        if (tets[4 * i] >= 0) {
+            for (int j = 0; j < 4; ++j)
+                for (int c = 0; c < 3; ++c) T[3 * j + c] = V[3 * (size_t)tets[4 * i + j] + c];
+            double a, b;
+            if (tet_dihedral(T, &a, &b)) { lo = a; hi = b; }
+        }
+        dmin[i] = lo;
+        dmax[i] = hi;
+    }
+}

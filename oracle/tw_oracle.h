@@ -45,6 +45,9 @@ void ora_amips_ring_ejh(const double *Vxyz, const int32_t *tets4, const int32_t 
 void ora_amips_ring_energy(const double *Vxyz, const int32_t *tets4, const int32_t *t_ids, const uint64_t *group_off,
                            uint64_t nGroups, double *E, int threads);
 
+/* calTetQuality_AD (LocalOperations.cpp:783-860); a tet with a negative first index is a removed slot -> (0, pi) */
+void ora_tet_dihedral(const double *Vxyz, const int32_t *tets4, uint64_t nT, double *dmin, double *dmax, int threads);
+
 /* ---- envelope (envelope.c) ---- */
 typedef struct ora_surface ora_surface;
 /* order: 0 = keep caller's facet order, 1 = sort facets along a Morton curve (stand-in for geogram mesh_reorder) */

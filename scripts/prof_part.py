@@ -40,6 +40,30 @@ def main():
         E = torch.empty(n, device="cuda", dtype=torch.float64); J = torch.empty(n, 3, device="cuda", dtype=torch.float64); H = torch.empty(n, 9, device="cuda", dtype=torch.float64)
         ptrs = [T[k].data_ptr() for k in range(12)]
         for _ in range(iters): ctx.amips_ejh_soa_dev(ptrs, E.data_ptr(), J.data_ptr(), H.data_ptr(), n, s)
+    elif part == "ring":
+        import bench
+        n = n or 16_000_000
+        dV, dT4, dOff, dCen = bench.rings_on_device(n, 7, torch.device("cuda", 0))
+        nG = dCen.numel()
+        E = torch.empty(nG, device="cuda", dtype=torch.float64); J = torch.empty(nG, 3, device="cuda", dtype=torch.float64); H = torch.empty(nG, 9, device="cuda", dtype=torch.float64)
+        K = torch.empty(nG, device="cuda", dtype=torch.uint8)
+        for _ in range(iters):
+            ctx.amips_ring_ejh_dev(dV.data_ptr(), dV.shape[0], dT4.data_ptr(), n, 0, dOff.data_ptr(), dCen.data_ptr(), nG, E.data_ptr(), J.data_ptr(), H.data_ptr(), K.data_ptr(), s)
+    elif part == "mesh":
+        # resident tet mesh: whole-mesh quality + dihedral passes and one-ring Newton terms for every vertex
+        g = n or 150
+        V, T = synth.grid_tet_mesh(g, g, g, seed=3)
+        M = tw.TetMesh(ctx, V, T)
+        nT, nV = len(T), len(V)
+        q = torch.empty(nT, device="cuda", dtype=torch.float64); a = torch.empty(nT, device="cuda", dtype=torch.float64); b = torch.empty(nT, device="cuda", dtype=torch.float64)
+        ids = torch.arange(nV, device="cuda", dtype=torch.int32)
+        E = torch.empty(nV, device="cuda", dtype=torch.float64); J = torch.empty(nV, 3, device="cuda", dtype=torch.float64); H = torch.empty(nV, 9, device="cuda", dtype=torch.float64)
+        K = torch.empty(nV, device="cuda", dtype=torch.uint8)
+        for _ in range(iters):
+            M.quality_dev(0, nT, q.data_ptr(), s)
+            M.dihedral_dev(0, nT, a.data_ptr(), b.data_ptr(), s)
+            M.vertex_ring_ejh_dev(ids.data_ptr(), nV, E.data_ptr(), J.data_ptr(), H.data_ptr(), K.data_ptr(), s)
+        n = nT
     elif part == "winding":
         n = n or 2_000_000
         V, F = synth.uv_sphere(708, 708)

@@ -86,3 +86,23 @@ def test_predicates(harness, oracle):
     z = [np.array(x, dtype=np.float64) for x in ([0, 0, 0], [1, 1, 1], [2, 2, 2], [2, 2, 2.0000000001])]
     assert harness.hh_triangle_is_degenerate(P(z[0]), P(z[1]), P(z[2])) == 1
     assert harness.hh_triangle_is_degenerate(P(z[0]), P(z[1]), P(z[3])) == 0
+
+
+def test_oracle_dihedral_known_answers(oracle):
+    """calTetQuality_AD (LocalOperations.cpp:783-860): regular tet -> acos(1/3) six times; corner tet -> three right
+    angles and three acos(1/sqrt 3); a vertex on the opposite plane or a degenerate plane -> (0, pi) (:790-798)."""
+    R = np.array([[0, 0, 0], [1, 0, 0], [.5, 3 ** .5 / 2, 0], [.5, 3 ** .5 / 6, 6 ** .5 / 3]])
+    Cn = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.]])
+    flat = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.]])
+    dup = np.array([[0, 0, 0], [1, 0, 0], [1, 0, 0], [0, 0, 1.]])
+    V = np.concatenate([R, Cn, flat, dup])
+    lo, hi = oracle.tet_dihedral(V, np.arange(16, dtype=np.int32).reshape(4, 4))
+    assert abs(lo[0] - np.arccos(1 / 3)) < 1e-14 and abs(hi[0] - np.arccos(1 / 3)) < 1e-14
+    assert abs(lo[1] - np.arccos(1 / 3 ** .5)) < 1e-14 and abs(hi[1] - np.pi / 2) < 1e-14
+    assert lo[2] == 0 and hi[2] == np.pi and lo[3] == 0 and hi[3] == np.pi
+    # angles of a tet sum to more than 2 pi and less than 3 pi; invariant under uniform scale and translation
+    from tetwild_b200 import synth
+    Vg, Tg = synth.grid_tet_mesh(5, 4, 3)
+    a, b = oracle.tet_dihedral(Vg, Tg)
+    a2, b2 = oracle.tet_dihedral(Vg * 37.0 + 5.0, Tg)
+    assert np.abs(a - a2).max() < 1e-9 and np.abs(b - b2).max() < 1e-9 and (a > 0).all() and (b < np.pi).all()

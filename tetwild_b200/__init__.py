@@ -8,6 +8,7 @@ raises loudly otherwise.
 from .api import (  # noqa: F401
     Context,
     Surface,
+    TetMesh,
     Winding,
     TetWildGPUError,
     lib_path,

@@ -51,6 +51,16 @@ def load_library():
     L.twg_destroy.restype = None
     L.twg_surface_destroy.restype = None
     L.twg_winding_destroy.restype = None
+    L.twg_mesh_destroy.argtypes = [_vp]
+    L.twg_mesh_destroy.restype = None
+    L.twg_mesh_num_vertices.argtypes = [_vp]
+    L.twg_mesh_num_vertices.restype = C.c_uint32
+    L.twg_mesh_num_tets.argtypes = [_vp]
+    L.twg_mesh_num_tets.restype = C.c_uint64
+    L.twg_mesh_vertices_dev.argtypes = [_vp]
+    L.twg_mesh_vertices_dev.restype = C.c_void_p
+    L.twg_mesh_tets_dev.argtypes = [_vp]
+    L.twg_mesh_tets_dev.restype = C.c_void_p
     _lib = L
     return L
 
@@ -272,6 +282,139 @@ class Surface:
         d = np.empty(len(P))
         self.ctx._check(self._L.twg_nearest(self.h, _ptr(P), C.c_uint64(len(P)), C.c_void_p(0), C.c_void_p(0), _ptr(d)))
         return d
+
+
+class TetMesh:
+    """twg_mesh: device-resident mirror of the scheduler's tet mesh -- `tet_vertices[].posf`, `tets`, `t_is_removed`,
+    `tet_vertices[].conn_tets` (src/tetwild/LocalOperations.h:35-45). A removed tet has a negative first index."""
+
+    def __init__(self, ctx, V, tets):
+        self.ctx = ctx
+        self._L = ctx._L
+        V = _f64(V)
+        tets = np.ascontiguousarray(tets, dtype=np.int32).reshape(-1, 4)
+        h = C.c_void_p()
+        ctx._check(self._L.twg_mesh_create(ctx.h, _ptr(V), C.c_uint32(len(V)), _ptr(tets), C.c_uint64(len(tets)), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._L.twg_mesh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def num_vertices(self):
+        return int(self._L.twg_mesh_num_vertices(self.h))
+
+    @property
+    def num_tets(self):
+        return int(self._L.twg_mesh_num_tets(self.h))
+
+    @property
+    def vertices_dev(self):
+        return int(self._L.twg_mesh_vertices_dev(self.h) or 0)
+
+    @property
+    def tets_dev(self):
+        return int(self._L.twg_mesh_tets_dev(self.h) or 0)
+
+    def resize(self, nV, nT):
+        self.ctx._check(self._L.twg_mesh_resize(self.h, C.c_uint32(nV), C.c_uint64(nT)))
+
+    def set_vertices(self, v_ids, xyz):
+        """posf[v_ids[i]] = xyz[i] (after an accepted smoothing / split / collapse)"""
+        ids = np.ascontiguousarray(v_ids, dtype=np.int32)
+        xyz = _f64(xyz).reshape(-1, 3)
+        assert len(ids) == len(xyz)
+        self.ctx._check(self._L.twg_mesh_set_vertices(self.h, _ptr(ids), _ptr(xyz), C.c_uint64(len(ids))))
+
+    def set_tets(self, t_ids, tets):
+        """tets[t_ids[i]] = tets[i]; a negative first index marks t_is_removed"""
+        ids = np.ascontiguousarray(t_ids, dtype=np.int32)
+        tets = np.ascontiguousarray(tets, dtype=np.int32).reshape(-1, 4)
+        assert len(ids) == len(tets)
+        self.ctx._check(self._L.twg_mesh_set_tets(self.h, _ptr(ids), _ptr(tets), C.c_uint64(len(ids))))
+
+    def get_vertices(self):
+        out = np.empty((self.num_vertices, 3))
+        self.ctx._check(self._L.twg_mesh_get_vertices(self.h, _ptr(out)))
+        return out
+
+    def build_rings(self):
+        self.ctx._check(self._L.twg_mesh_build_rings(self.h))
+
+    def get_rings(self):
+        """conn_tets as CSR: (off[nV+1], tets[off[nV]]), tets ascending within a vertex"""
+        off = np.empty(self.num_vertices + 1, dtype=np.uint64)
+        self.ctx._check(self._L.twg_mesh_get_rings(self.h, _ptr(off), C.c_void_p(0)))
+        t = np.empty(int(off[-1]), dtype=np.int32)
+        if len(t):
+            self.ctx._check(self._L.twg_mesh_get_rings(self.h, _ptr(off), _ptr(t)))
+        return off, t
+
+    def _tids(self, t_ids):
+        if t_ids is None:
+            return None, self.num_tets
+        ids = np.ascontiguousarray(t_ids, dtype=np.int32)
+        return ids, len(ids)
+
+    def quality(self, t_ids=None):
+        """calTetQuality_AMIPS over the resident mesh (LocalOperations.cpp:862-884); t_ids None = every slot"""
+        ids, n = self._tids(t_ids)
+        out = np.empty(n)
+        self.ctx._check(self._L.twg_mesh_quality(self.h, _ptr(ids), C.c_uint64(n), _ptr(out)))
+        return out
+
+    def quality_dev(self, dTids, n, dSlim, stream=0):
+        self.ctx._check(self._L.twg_mesh_quality_dev(self.h, _dev(dTids), C.c_uint64(n), _dev(dSlim), _dev(stream)))
+
+    def dihedral(self, t_ids=None):
+        """calTetQuality_AD (LocalOperations.cpp:783-860) -> (min_d_angle, max_d_angle)"""
+        ids, n = self._tids(t_ids)
+        lo, hi = np.empty(n), np.empty(n)
+        self.ctx._check(self._L.twg_mesh_dihedral(self.h, _ptr(ids), C.c_uint64(n), _ptr(lo), _ptr(hi)))
+        return lo, hi
+
+    def dihedral_dev(self, dTids, n, dMin, dMax, stream=0):
+        self.ctx._check(self._L.twg_mesh_dihedral_dev(self.h, _dev(dTids), C.c_uint64(n), _dev(dMin), _dev(dMax), _dev(stream)))
+
+    def vertex_ring_ejh(self, v_ids, out=None):
+        """NewtonsUpdate (VertexSmoother.cpp:627-702) for the one-rings conn_tets[v], v in v_ids"""
+        ids = np.ascontiguousarray(v_ids, dtype=np.int32)
+        g = len(ids)
+        if out is not None:
+            E, J, H, ok = out
+        else:
+            E, J, H, ok = np.empty(g), np.empty((g, 3)), np.empty((g, 9)), np.empty(g, dtype=np.uint8)
+        self.ctx._check(self._L.twg_mesh_vertex_ring_ejh(self.h, _ptr(ids), C.c_uint64(g), _ptr(E), _ptr(J), _ptr(H), _ptr(ok)))
+        return E, J, H, ok
+
+    def vertex_ring_ejh_dev(self, dVids, n, dE, dJ3, dH9, dOk, stream=0):
+        self.ctx._check(self._L.twg_mesh_vertex_ring_ejh_dev(self.h, _dev(dVids), C.c_uint64(n), _dev(dE), _dev(dJ3), _dev(dH9), _dev(dOk),
+                                                             _dev(stream)))
+
+    def ring_ejh(self, t_ids, group_off, center):
+        tid = np.ascontiguousarray(t_ids, dtype=np.int32)
+        off = np.ascontiguousarray(group_off, dtype=np.uint64)
+        center = np.ascontiguousarray(center, dtype=np.int32)
+        g = len(center)
+        E, J, H, ok = np.empty(g), np.empty((g, 3)), np.empty((g, 9)), np.empty(g, dtype=np.uint8)
+        self.ctx._check(self._L.twg_mesh_ring_ejh(self.h, _ptr(tid), _ptr(off), _ptr(center), C.c_uint64(g), _ptr(E), _ptr(J), _ptr(H), _ptr(ok)))
+        return E, J, H, ok
+
+    def ring_energy(self, t_ids, group_off):
+        tid = np.ascontiguousarray(t_ids, dtype=np.int32)
+        off = np.ascontiguousarray(group_off, dtype=np.uint64)
+        g = len(off) - 1
+        E = np.empty(g)
+        self.ctx._check(self._L.twg_mesh_ring_energy(self.h, _ptr(tid), _ptr(off), C.c_uint64(g), _ptr(E)))
+        return E
 
 
 class Winding:

@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) mesh_quality_kernel(const double* __restr
 // projection_planeC3; CGAL is not vendored, restated from its published kernel_ftC3.h): plain IEEE double, evaluated
 // here without contraction so that the arguments of acos are the doubles an x86-64 build without FMA produces.
 __device__ __forceinline__ bool tet_dihedral(const double* x, double& amin, double& amax) {
-    using namespace tw;
+    using tw::V3; using tw::mk; using tw::vdot; using tw::vlen2;
+    using tw::dadd; using tw::dsub; using tw::dmul; using tw::ddiv; using tw::dsqrt;  // hide CUDA's ::dadd(a, b, mode) family
     V3 nv[4];
     double len[4];
 #pragma unroll

@@ -228,6 +228,50 @@ def ring_groups(n_groups, seed=7, kmin=12, kmax=36, **kw):
     return V, out, off, np.arange(n_groups, dtype=np.int32)
 
 
+def grid_tet_mesh(nx, ny, nz, jitter=0.25, seed=13, shuffle=True):
+    """A connected tet mesh of the scheduler's shape (`tet_vertices[].posf`, `tets`): an (nx, ny, nz)-cell grid, every
+    cell cut into 6 tets along its main diagonal (Kuhn), vertices jittered by `jitter` cell widths (< 0.29 keeps
+    every tet positive). All tets are CGAL-POSITIVE; interior vertices have one-rings of 24 tets (the mean ring size
+    the reference reports). Returns (V[nV,3] f64, tets[nT,4] int32); tets and vertex slots randomly permuted."""
+    rng = np.random.default_rng(seed)
+    gx, gy, gz = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    V = np.stack([gx, gy, gz], -1).reshape(-1, 3).astype(np.float64)
+    V += rng.uniform(-jitter, jitter, V.shape)
+    V /= max(nx, ny, nz)
+
+    def vid(i, j, k):
+        return (i * (ny + 1) + j) * (nz + 1) + k
+
+    ci, cj, ck = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    ci, cj, ck = ci.ravel(), cj.ravel(), ck.ravel()
+    tets = []
+    import itertools
+    for perm in itertools.permutations(range(3)):
+        d = np.zeros((4, 3), dtype=np.int64)
+        for s, ax in enumerate(perm):
+            d[s + 1] = d[s]
+            d[s + 1, ax] += 1
+        corners = [vid(ci + d[s, 0], cj + d[s, 1], ck + d[s, 2]) for s in range(4)]
+        # orientation = sign of the permutation; swap two vertices of the odd ones
+        inv = sum(1 for a in range(3) for b in range(a + 1, 3) if perm[a] > perm[b])
+        if inv % 2 == 1:
+            corners[2], corners[3] = corners[3], corners[2]
+        tets.append(np.stack(corners, 1))
+    tets = np.concatenate(tets).astype(np.int32)
+    if shuffle:
+        tets = tets[rng.permutation(len(tets))]
+        pv = rng.permutation(len(V))          # new slot of old vertex i
+        Vn = np.empty_like(V)
+        Vn[pv] = V
+        V, tets = Vn, pv[tets].astype(np.int32)
+        # even permutations of the 4 slots keep orientation: rotate (1,2,3) at random
+        r = rng.integers(0, 3, len(tets))
+        for q in (1, 2):
+            m = r == q
+            tets[m, 1:] = np.roll(tets[m, 1:], q, axis=1)
+    return V, np.ascontiguousarray(tets)
+
+
 def winding_queries(V, n, seed=11, scale=1.2):
     rng = np.random.default_rng(seed)
     lo, hi = V.min(0), V.max(0)
