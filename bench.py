@@ -29,18 +29,20 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-FULL = {"envelope": 10_000_000, "amips": 50_000_000, "amips_ring": 50_000_000, "winding": 100_000_000}
-UNIT = {"envelope": "points/s", "amips": "tets/s", "amips_ring": "tets/s", "winding": "queries/s"}
+FULL = {"envelope": 10_000_000, "amips": 50_000_000, "amips_ring": 50_000_000, "winding": 100_000_000, "envelope_faces": 400_000}
+UNIT = {"envelope": "points/s", "amips": "tets/s", "amips_ring": "tets/s", "winding": "queries/s", "envelope_faces": "faces/s"}
 METRIC = {"envelope": "envelope points/s", "amips": "AMIPS E+J+H tet-evals/s", "amips_ring": "AMIPS one-ring E+J+H tet-evals/s",
-          "winding": "winding-number queries/s"}
+          "winding": "winding-number queries/s", "envelope_faces": "envelope faces/s (isFaceOutEnvelop)"}
+FACE_EDGE = 0.02  # C1-shaped candidate faces: small enough that the flat face stays within eps of the curved icosphere about half the time
 WORKLOAD = {
     "envelope": "C2: %d sampled points vs 200000-triangle (2,3) torus knot, eps_rel=1e-3 -> eps_2=(0.42265e-3)^2 (State.cpp:36-41)",
     "amips": "C3: %d random non-degenerate tets, flat SoA (12 arrays), E+J[3]+H[9] per tet, FP64",
     "amips_ring": "C3 smoothing-candidate layout: %d random non-degenerate tets in one-rings of k~U{12..36} around a centre vertex (indexed gather, centre rotated to slot 0), E+J[3]+H[9] per ring (NewtonsUpdate), FP64",
     "winding": "C4: %d centroids uniform in 1.2x bbox vs 1001112-triangle closed noisy UV sphere, keep = W > 0.5",
+    "envelope_faces": "C1-shaped call stream: %d candidate faces (edge ~ diag/50, sampled on the device at sampling_dist = 1e-3 diag like Common.cpp:143-255) vs the 20480-triangle icosphere, eps through State.cpp:36-41",
 }
 # algorithmic HBM bytes per unit (ring: 16 B indices + 72 B gathered vertices + 128 B of per-ring data / 24)
-ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "amips_ring": 93.0, "winding": 25.0}
+ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "amips_ring": 93.0, "winding": 25.0, "envelope_faces": 73.0}
 
 
 def peaks():
@@ -254,6 +256,18 @@ def cpu_rate(part, n_full, threads, budget_s=8.0):
         t = time.perf_counter(); fn(V, tets, off, cen, threads=threads); dt = time.perf_counter() - t
         what = "NewtonsUpdate restated around the reference's own LocalOperations.cpp:28-291 E/J/H text (oracle/ref_wrap.cpp)" if have_ref else "oracle port of NewtonsUpdate"
         return nt / dt, kind, "%d of %d tets in %d one-rings, %s, OpenMP over rings" % (nt, n_full, len(cen), what)
+    if part == "envelope_faces":
+        V, F = synth.icosphere(5)
+        V = synth.normalise_unit_diag(V)
+        sd, eps, eps2 = synth.state_eps(1e-3)
+        S = O.Surface(V, F)
+        T = synth.face_queries(V, F, 2000, FACE_EDGE, eps, seed=99)
+        t = time.perf_counter(); S.faces_out(T, sd, eps2, threads=threads); r0 = len(T) / (time.perf_counter() - t)
+        m = int(min(n_full, max(2000, r0 * budget_s)))
+        T = synth.face_queries(V, F, m, FACE_EDGE, eps, seed=3)
+        t = time.perf_counter(); S.faces_out(T, sd, eps2, threads=threads); dt = time.perf_counter() - t
+        return m / dt, "port", ("%d of %d faces, oracle port of isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109: sampleTriangle + "
+                                "facet_in_envelope_with_hint, first OUT sample stops the face), OpenMP over faces" % (m, n_full))
     if part == "winding":
         V, F = sphere_surface()
         WT = O.WindingTree(V, F)
@@ -314,6 +328,9 @@ def run_gpu(args, parts):
     torch.cuda.set_stream(stream)
     sh = stream.cuda_stream
     hbm_peak, peak_src = peaks()
+    # roofline denominators measured in this very run on this device (peaks.cu): FP64 DFMA rate and the library's own copy kernel
+    fp64_peak = ctx.measure_fp64_tflops()
+    copy_gbs = ctx.measure_copy_gbs(1 << 30)
     clocks = Clocks(local)
     if rank == 0:
         clocks.start()
@@ -398,6 +415,31 @@ def run_gpu(args, parts):
                                                            "surface_triangles": int(len(F))}})
             res["config"]["l2"] = "inputs larger than L2: 240 MB of points streamed per step; the 38 MB surface structure is meant to stay L2-resident"
             del dP, dO, S
+        elif part == "envelope_faces":
+            V, F = synth.icosphere(5)
+            V = synth.normalise_unit_diag(V)
+            sd, eps, eps2 = synth.state_eps(1e-3)
+            S = tw.Surface(ctx, V, F)
+            T = synth.face_queries(V, F, n, FACE_EDGE, eps, seed=3 + rank)
+            hT = torch.from_numpy(T).pin_memory()
+            dTr = hT.to(dev, non_blocking=True)
+            dO = torch.empty(n, device=dev, dtype=torch.uint8)
+            gath = [torch.empty(n, device=dev, dtype=torch.uint8) for _ in range(world)] if world > 1 else None
+            step = lambda: S.faces_out_dev(dTr.data_ptr(), n, sd, eps2, dO.data_ptr(), sh)  # noqa: E731
+            gfn = (lambda: dist.all_gather(gath, dO)) if world > 1 else None
+            ms, kms, launches, win = timed(step, gfn)
+            e2e_s = e2e_timed(lambda: S.faces_out(hT.numpy(), sd, eps2))
+            mism = nsamp = None
+            if rank == 0:
+                idx = np.random.default_rng(5).choice(n, min(n, 5000), replace=False)
+                ref, cnt = O.Surface(V, F).faces_out(T[idx], sd, eps2, threads=O.max_threads())
+                mism = int((ref != dO.cpu().numpy()[idx]).sum())
+                nsamp = float(np.mean(cnt))
+            res.update({"h2d": n * 72, "d2h": n, "extra": {"out_of_envelope_fraction": float(dO.float().mean().item()),
+                                                           "decision_mismatches_vs_oracle_5k_sample": mism,
+                                                           "mean_samples_per_face_sampleTriangle": nsamp, "surface_triangles": int(len(F))}})
+            res["config"]["l2"] = "L2 flushed by construction: every step re-reads %.0f MB of faces; the 4 MB surface structure stays L2-resident" % (n * 72 / 1e6)
+            del dTr, dO, S
         elif part == "amips":
             dT = tets_on_device(n, 7 + rank, dev)
             dE = torch.empty(n, device=dev, dtype=torch.float64)
@@ -437,7 +479,19 @@ def run_gpu(args, parts):
                                                   dJ.data_ptr(), dH.data_ptr(), dOk.data_ptr(), sh)
             ms, kms, launches, win = timed(step)
             hV, hT4, hOff, hCen = dV.cpu().pin_memory(), dT4.cpu().pin_memory(), dOff.cpu().pin_memory(), dCen.cpu().pin_memory()
-            e2e_s = e2e_timed(lambda: ctx.amips_ring_ejh(hV.numpy(), hT4.numpy(), hOff.numpy().view(np.uint64), hCen.numpy()))
+            ship_s = e2e_timed(lambda: ctx.amips_ring_ejh(hV.numpy(), hT4.numpy(), hOff.numpy().view(np.uint64), hCen.numpy()))
+            # the integration the scheduler uses: the tet mesh is RESIDENT on the device (uploaded once,
+            # kept in step by scatter updates), a Newton batch ships 4 B of vertex id per ring in and 105 B per ring out
+            t0 = time.perf_counter()
+            M = tw.TetMesh(ctx, hV.numpy(), hT4.numpy())
+            M.build_rings()
+            mesh_build_s = time.perf_counter() - t0
+            hE, hJ, hH = (torch.empty(sz, dtype=torch.float64).pin_memory() for sz in ((nG,), (nG, 3), (nG, 9)))
+            hOk = torch.empty(nG, dtype=torch.uint8).pin_memory()
+            outs = (hE.numpy(), hJ.numpy(), hH.numpy(), hOk.numpy())
+            e2e_s = e2e_timed(lambda: M.vertex_ring_ejh(hCen.numpy(), out=outs))
+            same = bool(np.array_equal(hE.numpy(), dE.cpu().numpy()) and np.array_equal(hH.numpy(), dH.cpu().numpy()))
+            M.close()
             mism = None
             if rank == 0:
                 gsel = np.random.default_rng(5).choice(nG, min(nG, 4000), replace=False)
@@ -453,8 +507,12 @@ def run_gpu(args, parts):
                 eH = np.abs(got[2] - Ho).max(1) / np.abs(Ho).max(1)
                 mism = {"max_rel_err_E": float(eE.max()), "max_rel_err_J_normwise": float(eJ.max()), "max_rel_err_H_normwise": float(eH.max()),
                         "ok_flag_mismatches": int((dOk.cpu().numpy()[gsel] != oko).sum()), "rings_checked": int(len(gsel))}
-            res.update({"h2d": nV * 24 + n * 16 + (nG + 1) * 8 + nG * 4, "d2h": nG * 105,
-                        "extra": {"rings": nG, "vertices": nV, "parity_vs_oracle": mism}})
+            res.update({"h2d": nG * 4, "d2h": nG * 105,
+                        "extra": {"rings": nG, "vertices": nV, "parity_vs_oracle": mism,
+                                  "e2e_path": "twg_mesh_vertex_ring_ejh on the resident tet mesh (host ids in, host E/J/H/ok out)",
+                                  "resident_results_identical_to_device_batch": same, "resident_mesh_upload_and_ring_build_s": mesh_build_s,
+                                  "e2e_ship_everything": {"value": n * world / ship_s, "unit": "tets/s", "path": "twg_amips_ring_ejh (vertices + tets + CSR shipped with every call)",
+                                                          "h2d_bytes_per_step": nV * 24 + n * 16 + (nG + 1) * 8 + nG * 4, "d2h_bytes_per_step": nG * 105}}})
             res["config"]["l2"] = "inputs larger than L2: %.1f GB of vertices + %.1f GB of indices gathered per step" % (nV * 24 / 1e9, n * 16 / 1e9)
             del dV, dT4, dOff, dCen, dE, dJ, dH, dOk, hV, hT4, hOff, hCen
         elif part == "winding":
@@ -491,7 +549,8 @@ def run_gpu(args, parts):
         res["e2e"] = {"value": total_units / e2e_s, "unit": UNIT[part], "h2d_bytes_per_step": res.pop("h2d"), "d2h_bytes_per_step": res.pop("d2h")}
         ach = ALG_BYTES[part] * n / (kms * 1e-3) / 1e9
         res["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
-                           "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_unit": ALG_BYTES[part]}
+                           "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_unit": ALG_BYTES[part],
+                           "fp64_dfma_peak_tflops_measured_in_run": fp64_peak, "copy_gbs_measured_in_run": copy_gbs}
         res["clocks"] = Clocks.summarise(clocks.window(*win)) if rank == 0 else None
         if rank == 0 and world == 1 and not args.no_cpu:
             v, kind, sample = cpu_rate(part, n, O.max_threads(), budget_s=args.cpu_budget)
@@ -537,7 +596,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--parts", default="envelope,amips,amips_ring,winding")
+    ap.add_argument("--parts", default="envelope,envelope_faces,amips,amips_ring,winding")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full BASELINE.json batch sizes (1.0 = as named)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=8.0)

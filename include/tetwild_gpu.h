@@ -82,6 +82,12 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
  * Writes at most cap points, *count = number the reference generates. */
 int twg_sample_triangle(twg_ctx* ctx, const double* tri9, double sampling_dist, double* out_xyz, uint64_t cap, uint64_t* count);
 
+/* ---- roofline denominators measured on the context's device (not on the hot path; bench.py calls them once) -------- */
+/* FP64 vector pipe: DFMA microbenchmark, 2 flops per DFMA, TFLOP/s.  Copy: 128-bit grid-stride copy, read+write GB/s. */
+int twg_measure_fp64_tflops(twg_ctx* ctx, double* tflops);
+int twg_measure_fp64_tflops_distinct(twg_ctx* ctx, double* tflops);  /* three distinct register operands per DFMA */
+int twg_measure_copy_gbs(twg_ctx* ctx, uint64_t bytes, double* gbs);
+
 /* ---- S1/S3: AMIPS ------------------------------------------------------------------------------------------------ */
 /* S1 mirror: exactly energy_ispc's argument list (12 SoA coordinate arrays, E, count) plus the context. */
 int twg_amips_energy_soa(twg_ctx* ctx, const double* const T[12], double* E, uint64_t n);

@@ -320,6 +320,108 @@ private:
 };
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * TetMesh: the scheduler's mesh kept resident on the device (twg_mesh, include/tetwild_gpu.h "resident tet mesh").
+ * Mirrors `tet_vertices[].posf`, `tets`, `t_is_removed` and `tet_vertices[].conn_tets` (LocalOperations.h:35-45): create
+ * once after the front end (MeshRefinement.cpp:208), call sync_vertices / sync_tets for what an accepted operation
+ * changed, and the AMIPS batches of a pass then ship only ids in and results out.
+ *   POS: callable  const double* pos(int v_id)  -> the 3 doubles of tet_vertices[v_id].posf
+ * ---------------------------------------------------------------------------------------------------------------- */
+class TetMesh {
+public:
+    template <class POS>
+    TetMesh(Context& ctx, size_t n_vertices, POS pos, const std::vector<std::array<int, 4> >& tets, const std::vector<bool>& t_is_removed)
+        : ctx_(ctx), m_(nullptr) {
+        std::vector<double> V(3 * n_vertices);
+        for (size_t v = 0; v < n_vertices; ++v) {
+            const double* p = pos((int)v);
+            V[3 * v] = p[0]; V[3 * v + 1] = p[1]; V[3 * v + 2] = p[2];
+        }
+        std::vector<int32_t> T(4 * tets.size());
+        for (size_t t = 0; t < tets.size(); ++t) pack(tets[t], t < t_is_removed.size() && t_is_removed[t], &T[4 * t]);
+        ctx_.check(twg_mesh_create(ctx_.handle(), V.data(), (uint32_t)n_vertices, T.data(), tets.size(), &m_));
+    }
+    ~TetMesh() { twg_mesh_destroy(m_); }
+    twg_mesh* handle() const { return m_; }
+    size_t num_vertices() const { return twg_mesh_num_vertices(m_); }
+    size_t num_tets() const { return (size_t)twg_mesh_num_tets(m_); }
+
+    /* after tet_vertices / tets grew (EdgeSplitter pushes new slots, EdgeSplitter.cpp:130-147) */
+    void resize(size_t n_vertices, size_t n_tets) { ctx_.check(twg_mesh_resize(m_, (uint32_t)n_vertices, n_tets)); }
+    /* posf of the listed vertices changed (accepted smoothing step, VertexSmoother.cpp:139-150; split / collapse) */
+    template <class POS>
+    void sync_vertices(const std::vector<int>& v_ids, POS pos) {
+        std::vector<double> xyz(3 * v_ids.size());
+        for (size_t i = 0; i < v_ids.size(); ++i) {
+            const double* p = pos(v_ids[i]);
+            xyz[3 * i] = p[0]; xyz[3 * i + 1] = p[1]; xyz[3 * i + 2] = p[2];
+        }
+        ctx_.check(twg_mesh_set_vertices(m_, v_ids.data(), xyz.data(), v_ids.size()));
+    }
+    /* the listed tet slots were rewritten or removed */
+    void sync_tets(const std::vector<int>& t_ids, const std::vector<std::array<int, 4> >& tets, const std::vector<bool>& t_is_removed) {
+        std::vector<int32_t> T(4 * t_ids.size());
+        for (size_t i = 0; i < t_ids.size(); ++i) {
+            const size_t t = (size_t)t_ids[i];
+            pack(tets[t], t < t_is_removed.size() && t_is_removed[t], &T[4 * i]);
+        }
+        ctx_.check(twg_mesh_set_tets(m_, t_ids.data(), T.data(), t_ids.size()));
+    }
+
+    /* calTetQuality_AMIPS of the listed tets (LocalOperations.cpp:862-884); the whole-mesh loops of
+     * VertexSmoother.cpp:216-241 and MeshRefinement.cpp:51 pass every live tet id */
+    void calTetQualities(const std::vector<int>& t_ids, std::vector<TetQuality>& tet_qs) const {
+        std::vector<double> e(t_ids.size());
+        tet_qs.resize(t_ids.size());
+        if (t_ids.empty()) return;
+        ctx_.check(twg_mesh_quality(m_, t_ids.data(), t_ids.size(), e.data()));
+        for (size_t i = 0; i < e.size(); ++i) tet_qs[i].slim_energy = e[i];
+    }
+    /* calTetQuality_AD (LocalOperations.cpp:783-860) of the listed tets */
+    void calTetQuality_AD(const std::vector<int>& t_ids, std::vector<double>& min_d_angle, std::vector<double>& max_d_angle) const {
+        min_d_angle.resize(t_ids.size()); max_d_angle.resize(t_ids.size());
+        if (t_ids.empty()) return;
+        ctx_.check(twg_mesh_dihedral(m_, t_ids.data(), t_ids.size(), min_d_angle.data(), max_d_angle.data()));
+    }
+    /* VertexSmoother::NewtonsUpdate (VertexSmoother.cpp:627-702) for the one-rings conn_tets[v] of many vertices */
+    void NewtonsUpdate(const std::vector<int>& v_ids, std::vector<double>& energy, std::vector<double>& J3, std::vector<double>& H9,
+                       std::vector<uint8_t>& ok) const {
+        const size_t g = v_ids.size();
+        energy.resize(g); J3.resize(3 * g); H9.resize(9 * g); ok.resize(g);
+        if (g) ctx_.check(twg_mesh_vertex_ring_ejh(m_, v_ids.data(), g, energy.data(), J3.data(), H9.data(), ok.data()));
+    }
+    /* one vertex with the reference's own member list (t_ids = conn_tets[v_id]) */
+    bool NewtonsUpdate(const std::vector<int>& t_ids, int v_id, double& energy, double* J, double* H) const {
+        const uint64_t off[2] = {0, (uint64_t)t_ids.size()};
+        uint8_t ok = 0;
+        ctx_.check(twg_mesh_ring_ejh(m_, t_ids.data(), off, &v_id, 1, &energy, J, H, &ok));
+        return ok != 0;
+    }
+    /* VertexSmoother::getNewEnergy (VertexSmoother.cpp:544-625) */
+    double getNewEnergy(const std::vector<int>& t_ids) const {
+        const uint64_t off[2] = {0, (uint64_t)t_ids.size()};
+        double e = 0;
+        ctx_.check(twg_mesh_ring_energy(m_, t_ids.data(), off, 1, &e));
+        return e;
+    }
+    /* conn_tets as the device rebuilt it: ring of vertex v = tets[off[v] .. off[v+1]) in ascending tet id */
+    void conn_tets(std::vector<uint64_t>& off, std::vector<int>& tets) const {
+        off.resize(num_vertices() + 1);
+        ctx_.check(twg_mesh_get_rings(m_, off.data(), nullptr));
+        tets.resize((size_t)off.back());
+        if (!tets.empty()) ctx_.check(twg_mesh_get_rings(m_, off.data(), tets.data()));
+    }
+
+private:
+    TetMesh(const TetMesh&);
+    TetMesh& operator=(const TetMesh&);
+    static void pack(const std::array<int, 4>& t, bool removed, int32_t* out) {
+        out[0] = removed ? -1 : t[0]; out[1] = t[1]; out[2] = t[2]; out[3] = t[3];
+    }
+    Context& ctx_;
+    twg_mesh* m_;
+};
+
+/* ------------------------------------------------------------------------------------------------------------------
  * igl::winding_number(V, F, O, W) (called at InoutFiltering.cpp:45,66; MeshRefinement.cpp:614,1056).
  * MATD / MATI / VECD: Eigen-like (rows(), cols(), operator()(i,j), resize(n)); any storage order.
  * ---------------------------------------------------------------------------------------------------------------- */

@@ -29,7 +29,7 @@ def main():
     Ph = bench.envelope_points_fast(V, F, n, eps, seed=20240501)
     P = torch.from_numpy(Ph).cuda()
     O = torch.empty(n, device="cuda", dtype=torch.uint8)
-    res = {"hint": os.environ.get("TWG_ENV_HINT", "1"), "n": n}
+    res = {"policy": os.environ.get("TWG_ENV_POLICY", "1"), "group": os.environ.get("TWG_ENV_GROUP", "64"), "n": n}
     for name, e2 in (("env_state_eps", eps2), ("env_1e-3", 1e-6)):
         t = timeit(lambda: S.points_out_dev(P.data_ptr(), n, e2, O.data_ptr(), s))
         res[name] = dict(ms=t[0], med=t[1], gpts_s=n / t[0] / 1e6, out_frac=float(O.float().mean()))
@@ -37,6 +37,9 @@ def main():
         idx = np.random.default_rng(1).choice(n, m, replace=False)
         ref = oracle.Surface(V, F).points_out(Ph[idx], e2, threads=16)
         res[name]["mismatch_100k"] = int((O.cpu().numpy()[idx] != ref).sum())
+    if os.environ.get("ENV_AB_SKIP_NEAREST"):
+        print(json.dumps(res))
+        return
     D = torch.empty(n, device="cuda", dtype=torch.float64)
     t = timeit(lambda: S.nearest_dev(P.data_ptr(), n, 0, 0, D.data_ptr(), s), iters=3, warm=1)
     res["nearest"] = dict(ms=t[0], mpts_s=n / t[0] / 1e3)

@@ -21,7 +21,7 @@ def main():
             n = n or 20000
             T = torch.from_numpy(synth.face_queries(V, F, n, 0.05, eps)).cuda()
             O = torch.empty(n, device="cuda", dtype=torch.uint8)
-            for _ in range(iters): S.faces_out_dev(T.data_ptr(), n, sd, eps2, O.data_ptr(), s)
+            fn = lambda: S.faces_out_dev(T.data_ptr(), n, sd, eps2, O.data_ptr(), s)
         else:
             n = n or 10_000_000
             sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -29,17 +29,20 @@ def main():
             P = torch.from_numpy(bench.envelope_points_fast(V, F, n, eps, seed=20240501)).cuda()
             O = torch.empty(n, device="cuda", dtype=torch.uint8)
             if part == "envelope":
-                for _ in range(iters): S.points_out_dev(P.data_ptr(), n, eps2, O.data_ptr(), s)
+                fn = lambda: S.points_out_dev(P.data_ptr(), n, eps2, O.data_ptr(), s)
             else:
                 D = torch.empty(n, device="cuda", dtype=torch.float64)
-                for _ in range(iters): S.nearest_dev(P.data_ptr(), n, 0, 0, D.data_ptr(), s)
+                fn = lambda: S.nearest_dev(P.data_ptr(), n, 0, 0, D.data_ptr(), s)
     elif part == "amips":
         import bench
         n = n or 16_000_000
         T = bench.tets_on_device(n, 7, torch.device("cuda", 0))
         E = torch.empty(n, device="cuda", dtype=torch.float64); J = torch.empty(n, 3, device="cuda", dtype=torch.float64); H = torch.empty(n, 9, device="cuda", dtype=torch.float64)
         ptrs = [T[k].data_ptr() for k in range(12)]
-        for _ in range(iters): ctx.amips_ejh_soa_dev(ptrs, E.data_ptr(), J.data_ptr(), H.data_ptr(), n, s)
+        fn = lambda: ctx.amips_ejh_soa_dev(ptrs, E.data_ptr(), J.data_ptr(), H.data_ptr(), n, s)
+    elif part == "peaks":
+        n = 1
+        fn = lambda: print("fp64 TFLOP/s", ctx.measure_fp64_tflops(), "distinct-operand", ctx.measure_fp64_tflops_distinct(), "copy GB/s", ctx.measure_copy_gbs(1 << 30))
     elif part == "ring":
         import bench
         n = n or 16_000_000
@@ -47,8 +50,7 @@ def main():
         nG = dCen.numel()
         E = torch.empty(nG, device="cuda", dtype=torch.float64); J = torch.empty(nG, 3, device="cuda", dtype=torch.float64); H = torch.empty(nG, 9, device="cuda", dtype=torch.float64)
         K = torch.empty(nG, device="cuda", dtype=torch.uint8)
-        for _ in range(iters):
-            ctx.amips_ring_ejh_dev(dV.data_ptr(), dV.shape[0], dT4.data_ptr(), n, 0, dOff.data_ptr(), dCen.data_ptr(), nG, E.data_ptr(), J.data_ptr(), H.data_ptr(), K.data_ptr(), s)
+        fn = lambda: ctx.amips_ring_ejh_dev(dV.data_ptr(), dV.shape[0], dT4.data_ptr(), n, 0, dOff.data_ptr(), dCen.data_ptr(), nG, E.data_ptr(), J.data_ptr(), H.data_ptr(), K.data_ptr(), s)
     elif part == "mesh":
         # resident tet mesh: whole-mesh quality + dihedral passes and one-ring Newton terms for every vertex
         g = n or 150
@@ -59,7 +61,7 @@ def main():
         ids = torch.arange(nV, device="cuda", dtype=torch.int32)
         E = torch.empty(nV, device="cuda", dtype=torch.float64); J = torch.empty(nV, 3, device="cuda", dtype=torch.float64); H = torch.empty(nV, 9, device="cuda", dtype=torch.float64)
         K = torch.empty(nV, device="cuda", dtype=torch.uint8)
-        for _ in range(iters):
+        def fn():
             M.quality_dev(0, nT, q.data_ptr(), s)
             M.dihedral_dev(0, nT, a.data_ptr(), b.data_ptr(), s)
             M.vertex_ring_ejh_dev(ids.data_ptr(), nV, E.data_ptr(), J.data_ptr(), H.data_ptr(), K.data_ptr(), s)
@@ -70,9 +72,14 @@ def main():
         W = tw.Winding(ctx, V, F)
         Q = torch.from_numpy(synth.winding_queries(V, n, seed=11)).cuda()
         K = torch.empty(n, device="cuda", dtype=torch.uint8)
-        for _ in range(iters): W.eval_dev(Q.data_ptr(), n, 0, K.data_ptr(), s)
-    torch.cuda.synchronize()
-    print("done", part, n)
+        fn = lambda: W.eval_dev(Q.data_ptr(), n, 0, K.data_ptr(), s)
+    st = torch.cuda.current_stream()
+    ts = []
+    for _ in range(iters):
+        a0, b0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(st); fn(); b0.record(st); torch.cuda.synchronize()
+        ts.append(a0.elapsed_time(b0))
+    print("done %s n=%d iters=%d ms_min=%.4f ms_med=%.4f units_per_s=%.4g (CUDA events; meaningless under ncu)" % (part, n, iters, min(ts), float(np.median(ts)), n / min(ts) * 1e3))
 
 if __name__ == "__main__":
     main()

@@ -233,6 +233,64 @@ int main() {
             EXPECT(sm.getNewEnergy(ring) == En[g], "single-ring getNewEnergy differs at %zu", g);
         }
     }
+    // ---------------- resident tet mesh: the same answers with only ids crossing the bus ----------------
+    {
+        std::vector<bool> removed(tets.size(), false);
+        for (size_t i = 0; i < tets.size(); i += 13) removed[i] = true;
+        auto posf = [&](int v) { return &V[3 * (size_t)v]; };
+        twg::TetMesh mesh(ctx, nV, posf, tets, removed);
+        EXPECT(mesh.num_vertices() == (size_t)nV && mesh.num_tets() == tets.size(), "TetMesh sizes");
+        std::vector<int> live;
+        for (size_t i = 0; i < tets.size(); ++i)
+            if (!removed[i]) live.push_back((int)i);
+        std::vector<twg::TetQuality> q2;
+        mesh.calTetQualities(live, q2);
+        for (size_t k = 0; k < live.size(); ++k) EXPECT(q2[k].slim_energy == tet_qs[live[k]].slim_energy, "resident calTetQualities differs at tet %d", live[k]);
+        std::vector<double> amin, amax, omin(tets.size()), omax(tets.size());
+        mesh.calTetQuality_AD(live, amin, amax);
+        ora_tet_dihedral(V.data(), reinterpret_cast<const int32_t*>(tets.data()), tets.size(), omin.data(), omax.data(), 4);
+        for (size_t k = 0; k < live.size(); ++k)
+            EXPECT(std::fabs(amin[k] - omin[live[k]]) < 1e-13 && std::fabs(amax[k] - omax[live[k]]) < 1e-13, "calTetQuality_AD differs at tet %d", live[k]);
+        // conn_tets rebuilt on the device == the scheduler's own bookkeeping
+        std::vector<uint64_t> coff;
+        std::vector<int> ctets;
+        mesh.conn_tets(coff, ctets);
+        std::vector<std::vector<int> > conn(nV);
+        for (size_t i = 0; i < tets.size(); ++i)
+            if (!removed[i])
+                for (int k = 0; k < 4; ++k) conn[tets[i][k]].push_back((int)i);
+        size_t bad = 0;
+        for (int v = 0; v < nV; ++v) {
+            if (coff[v + 1] - coff[v] != conn[v].size()) { ++bad; continue; }
+            for (size_t k = 0; k < conn[v].size(); ++k) bad += ctets[coff[v] + k] != conn[v][k];
+        }
+        EXPECT(bad == 0, "conn_tets differs at %zu places", bad);
+        // NewtonsUpdate of a vertex through the resident mesh == through the ship-everything adapter (same kernel)
+        for (int v = 0; v < 20; ++v) {
+            if (conn[v].empty()) continue;
+            bool dup = false;  // a random tet may name v twice; the reference never has such tets
+            for (int t : conn[v]) { int c = 0; for (int k = 0; k < 4; ++k) c += tets[t][k] == v; dup = dup || c > 1; }
+            if (dup) continue;
+            double e1, j1[3], h1[9], e2, j2[3], h2[9];
+            const bool g1 = sm.NewtonsUpdate(conn[v], v, e1, j1, h1), g2 = mesh.NewtonsUpdate(conn[v], v, e2, j2, h2);
+            EXPECT(g1 == g2 && (e1 == e2 || (e1 != e1 && e2 != e2)), "resident NewtonsUpdate differs at vertex %d", v);
+            if (g1) EXPECT(j1[1] == j2[1] && h1[5] == h2[5], "resident NewtonsUpdate J/H differ at vertex %d", v);
+            const double n1 = sm.getNewEnergy(conn[v]), n2 = mesh.getNewEnergy(conn[v]);
+            EXPECT(n1 == n2, "resident getNewEnergy differs at vertex %d", v);
+        }
+        // an accepted smoothing step moves a vertex: sync and re-evaluate
+        V[3 * 5] += 0.01; V[3 * 5 + 2] -= 0.02;
+        mesh.sync_vertices(std::vector<int>(1, 5), posf);
+        std::vector<twg::TetQuality> qa, qb;
+        std::vector<int> ring5;
+        for (int t : conn[5]) ring5.push_back(t);
+        mesh.calTetQualities(ring5, qa);
+        std::vector<std::array<int, 4> > sub;
+        for (int t : ring5) sub.push_back(tets[t]);
+        lo.calTetQualities(V.data(), nV, sub, qb);
+        for (size_t k = 0; k < ring5.size(); ++k) EXPECT(qa[k].slim_energy == qb[k].slim_energy, "after sync_vertices: tet %d differs", ring5[k]);
+        V[3 * 5] -= 0.01; V[3 * 5 + 2] += 0.02;
+    }
     // energy_ispc argument list (LocalOperations.cpp:750)
     {
         const int n = 5000;

@@ -111,6 +111,22 @@ class Context:
     def synchronize(self):
         self._check(self._L.twg_synchronize(self.h))
 
+    # ---- roofline denominators (microbenchmarks, not on the hot path) ----
+    def measure_fp64_tflops(self):
+        v = C.c_double(0)
+        self._check(self._L.twg_measure_fp64_tflops(self.h, C.byref(v)))
+        return v.value
+
+    def measure_fp64_tflops_distinct(self):
+        v = C.c_double(0)
+        self._check(self._L.twg_measure_fp64_tflops_distinct(self.h, C.byref(v)))
+        return v.value
+
+    def measure_copy_gbs(self, nbytes=1 << 30):
+        v = C.c_double(0)
+        self._check(self._L.twg_measure_copy_gbs(self.h, C.c_uint64(nbytes), C.byref(v)))
+        return v.value
+
     # ---- AMIPS ----
     @staticmethod
     def _soa_ptrs(T):

@@ -133,76 +133,151 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
-// NewtonsUpdate (VertexSmoother.cpp:627-702): one warp per one-ring
+// NewtonsUpdate (VertexSmoother.cpp:627-702) / getNewEnergy (:544-625): one warp per one-ring, lanes over member tets.
+//
+// The address chain of a ring is four dependent loads deep (vids[g] -> off[row] -> t_ids[k] -> tets[ti] -> V[v]) and a ring
+// gives a warp only ~24 tets of arithmetic, so the kernel is a SOFTWARE PIPELINE over the warp's rings: while ring i is
+// gathered and evaluated, the tet records of ring i+1, the member ids of ring i+2, the CSR bounds of ring i+3 and the row of
+// ring i+4 are in flight (each stage consumes what the previous iteration loaded). Only the vertex gather of the current
+// ring is waited for.
+//   * the centre vertex is rotated to slot 0 (:640-651), so it is the same vertex for every member: loaded once per ring;
+//   * the closed-form Hessian is symmetric: 10 sums per ring (E, J[3], H[6]), reduced through a per-warp shared-memory
+//     transpose (10 stores + 16 loads per lane) instead of 13 x 5 64-bit shuffle steps; lane (c, h) adds the members
+//     16h .. 16h+15 of component c in lane order, the two halves meet in one shuffle -- deterministic, and closer to the
+//     reference's sequential ring order than a butterfly.
+struct RingHead {   // stage result: CSR bounds and centre of one ring (member offsets fit 32 bits: at most 4 * 2^29 members)
+    uint32_t b, cnt;
+    int32_t c;
+};
+
 template <bool ENERGY_ONLY>
-__global__ void __launch_bounds__(256) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
-                                                         const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
-                                                         const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
-                                                         double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
-                                                         uint8_t* __restrict__ ok) {
-    const int lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
+                                                            const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
+                                                            const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
+                                                            double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
+                                                            uint8_t* __restrict__ ok) {
+    constexpr int NRED = ENERGY_ONLY ? 1 : 10;
+    __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t g = warp; g < nG; g += nwarps) {
-        // vids != NULL: group g is the one-ring of vertex vids[g] in a vertex -> tets CSR (conn_tets of the resident mesh)
-        const uint64_t row = vids ? (uint64_t)__ldg(vids + g) : g;
+    const uint64_t gl = nG - 1;  // prefetches past the end re-read the last ring (valid addresses, never consumed)
+
+    // ---- pipeline stages: straight-line, every load unconditional or predicated (no branches)
+    auto stage_row = [&](uint64_t g) -> uint32_t {  // vids != NULL: ring g is the one-ring of vertex vids[g] in a vertex -> tets CSR
+        const uint64_t gg = g < gl ? g : gl;
+        return vids ? (uint32_t)__ldg(vids + gg) : (uint32_t)gg;
+    };
+    auto stage_head = [&](uint64_t g, uint32_t row) -> RingHead {
+        const uint64_t gg = g < gl ? g : gl;
         const uint64_t b = __ldg(off + row), e = __ldg(off + row + 1);
-        const int32_t c = vids ? (int32_t)row : (ENERGY_ONLY ? 0 : __ldg(center + g));
-        double acc[13];
-#pragma unroll
-        for (int k = 0; k < 13; ++k) acc[k] = 0.0;
-        for (uint64_t k = b + lane; k < e; k += 32) {
-            const uint64_t ti = t_ids ? (uint64_t)__ldg(t_ids + k) : k;
-            const int4 t = __ldg(tets + ti);
-            int32_t v[4] = {t.x, t.y, t.z, t.w};
-            int start = 0;
-            if (!ENERGY_ONLY) {  // :640-646, first slot holding the center vertex
-                if (v[0] == c) start = 0;
-                else if (v[1] == c) start = 1;
-                else if (v[2] == c) start = 2;
-                else if (v[3] == c) start = 3;
-            }
-            double x[12];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int32_t vj = (start == 0) ? v[j] : (start == 1) ? v[(j + 1) & 3] : (start == 2) ? v[(j + 2) & 3] : v[(j + 3) & 3];
-                gather_vertex(V, vj, x + 3 * j);
-            }
-            tw::Amips r;
-            tw::amips_eval<!ENERGY_ONLY>(x, r);
-            acc[0] += r.E;
-            if (!ENERGY_ONLY) {
-                acc[1] += r.J[0]; acc[2] += r.J[1]; acc[3] += r.J[2];
-                acc[4] += r.H[0]; acc[5] += r.H[1]; acc[6] += r.H[2];
-                acc[7] += r.H[1]; acc[8] += r.H[3]; acc[9] += r.H[4];
-                acc[10] += r.H[2]; acc[11] += r.H[4]; acc[12] += r.H[5];
-            }
-        }
-        acc[0] = warp_sum(acc[0]);
+        RingHead h;
+        h.b = (uint32_t)b; h.cnt = (uint32_t)(e - b);
+        h.c = vids ? (int32_t)row : (ENERGY_ONLY ? 0 : __ldg(center + gg));
+        return h;
+    };
+    auto stage_tid = [&](const RingHead& h, uint32_t k) -> uint32_t {  // member k of the ring -> tet id
+        const bool in = k < h.cnt;
+        return t_ids ? (in ? (uint32_t)__ldg(t_ids + h.b + k) : 0u) : h.b + (in ? k : 0u);
+    };
+    auto stage_tet = [&](const RingHead& h, uint32_t k, uint32_t ti) -> int4 {
+        int4 t = make_int4(0, 0, 0, 0);
+        if (k < h.cnt) t = __ldg(tets + ti);
+        return t;
+    };
+    // one member tet: gather, evaluate, add into the lane's partial sums
+    auto member = [&](int4 t, int32_t c, double* acc) {
+        int32_t a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
         if (!ENERGY_ONLY) {
-#pragma unroll
-            for (int k = 1; k < 13; ++k) acc[k] = warp_sum(acc[k]);
+            // :640-651, rotate so that the first slot holding the centre vertex comes first (slot 0 when absent, like the
+            // reference); getNewEnergy keeps the stored order. Two conditional register rotations: no branches, no indexing.
+            const int start = (a0 == c) ? 0 : (a1 == c) ? 1 : (a2 == c) ? 2 : (a3 == c) ? 3 : 0;
+            const bool r1 = (start & 1) != 0, r2 = (start & 2) != 0;
+            const int32_t b0 = r1 ? a1 : a0, b1 = r1 ? a2 : a1, b2 = r1 ? a3 : a2, b3 = r1 ? a0 : a3;
+            a0 = r2 ? b2 : b0; a1 = r2 ? b3 : b1; a2 = r2 ? b0 : b2; a3 = r2 ? b1 : b3;
         }
-        if (lane == 0) {
-            double en = acc[0];
-            if (ENERGY_ONLY) {  // getNewEnergy :619-622
+        double x[12];
+        gather_vertex(V, a0, x);  // the centre: the same address in every lane, one L1 transaction
+        gather_vertex(V, a1, x + 3);
+        gather_vertex(V, a2, x + 6);
+        gather_vertex(V, a3, x + 9);
+        tw::Amips r;
+        tw::amips_eval<!ENERGY_ONLY>(x, r);
+        acc[0] += r.E;
+        if (!ENERGY_ONLY) {
+            acc[1] += r.J[0]; acc[2] += r.J[1]; acc[3] += r.J[2];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[4 + k] += r.H[k];
+        }
+    };
+
+    // ---- prologue: fill the pipeline for rings i = 0 .. 3 of this warp
+    uint64_t g = warp;
+    RingHead h_cur = stage_head(g, stage_row(g));
+    int4 tet_cur = stage_tet(h_cur, lane, stage_tid(h_cur, lane));
+    RingHead h_n1 = stage_head(g + nwarps, stage_row(g + nwarps));
+    uint32_t ti_n1 = stage_tid(h_n1, lane);
+    RingHead h_n2 = stage_head(g + 2 * nwarps, stage_row(g + 2 * nwarps));
+    uint32_t row_n3 = stage_row(g + 3 * nwarps);
+
+    for (; g < nG; g += nwarps) {
+        // ---- issue the loads of the later rings first
+        const uint32_t row_n4 = stage_row(g + 4 * nwarps);
+        const RingHead h_n3 = stage_head(g + 3 * nwarps, row_n3);
+        const uint32_t ti_n2 = stage_tid(h_n2, lane);
+        const int4 tet_n1 = stage_tet(h_n1, lane, ti_n1);
+        // ---- ring g
+        double acc[NRED];
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+        if ((uint32_t)lane < h_cur.cnt) member(tet_cur, h_cur.c, acc);
+        for (uint32_t k = 32 + lane; k < h_cur.cnt; k += 32)  // rings of more than 32 tets: the rest is fetched on demand
+            member(stage_tet(h_cur, k, stage_tid(h_cur, k)), h_cur.c, acc);
+        if (ENERGY_ONLY) {
+            double en = warp_sum(acc[0]);
+            if (lane == 0) {  // getNewEnergy :619-622
                 if (isinf(en) || isnan(en) || en <= 0.0 || en > TWG_MAX_ENERGY) en = TWG_MAX_ENERGY;
                 E[g] = en;
-            } else {  // :680-699
-                bool good = true;
-                if (isinf(en)) en = TWG_MAX_ENERGY;
-                if (isnan(en)) good = false;
-                if (en <= 0.0) good = false;
+            }
+        } else {
 #pragma unroll
-                for (int k = 1; k < 13; ++k)
-                    if (!isfinite(acc[k])) good = false;
-                E[g] = en;
-                J3[g * 3 + 0] = acc[1]; J3[g * 3 + 1] = acc[2]; J3[g * 3 + 2] = acc[3];
+            for (int k = 0; k < NRED; ++k) red[wib][k][lane] = acc[k];
+            __syncwarp();
+            const int cmp = lane & 15, half = lane >> 4;
+            double sum = 0.0;
+            if (cmp < NRED) {
 #pragma unroll
-                for (int k = 0; k < 9; ++k) H9[g * 9 + k] = acc[4 + k];
-                if (ok) ok[g] = good ? 1 : 0;
+                for (int j = 0; j < 16; ++j) sum += red[wib][cmp][half * 16 + j];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+            __syncwarp();
+            // :680-699 -- E: +inf -> MAX_ENERGY, NaN or <= 0 rejects; any non-finite J / H rejects
+            bool bad = false;
+            if (cmp == 0) {
+                if (isinf(sum)) sum = TWG_MAX_ENERGY;
+                bad = isnan(sum) || sum <= 0.0;
+            } else if (cmp < NRED) {
+                bad = !isfinite(sum);
+            }
+            const bool good = !__any_sync(0xffffffffu, bad);
+            if (half == 0) {
+                if (cmp == 0) { E[g] = sum; if (ok) ok[g] = good ? 1 : 0; }
+                else if (cmp < 4) J3[g * 3 + (cmp - 1)] = sum;
+                else if (cmp < NRED) {
+                    // H6 = xx xy xz yy yz zz -> row-major 3x3: first slot of every component, mirror of the off-diagonal ones
+                    const int s0 = (cmp == 4) ? 0 : (cmp == 5) ? 1 : (cmp == 6) ? 2 : (cmp == 7) ? 4 : (cmp == 8) ? 5 : 8;
+                    const int s1 = (cmp == 5) ? 3 : (cmp == 6) ? 6 : (cmp == 8) ? 7 : s0;
+                    double* Hg = H9 + g * 9;
+                    Hg[s0] = sum;
+                    Hg[s1] = sum;
+                }
             }
         }
+        // ---- advance the pipeline
+        h_cur = h_n1; tet_cur = tet_n1;
+        h_n1 = h_n2; ti_n1 = ti_n2;
+        h_n2 = h_n3;
+        row_n3 = row_n4;
     }
 }
 
@@ -241,6 +316,12 @@ unsigned grid_for(twg_ctx* c, uint64_t items, int per_block, int waves) {
     return (unsigned)b;
 }
 
+// persistent grid of the ring kernels: 3 resident CTAs per SM (80 registers x 256 threads), every warp pipelines over its rings
+int ring_waves() {
+    static const int w = [] { const char* e = getenv("TWG_RING_WAVES"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : v; }();
+    return w;
+}
+
 }  // namespace
 
 extern "C" {
@@ -275,7 +356,7 @@ int twg_amips_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int3
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nG == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
+    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves()), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
                dCenter, (const int32_t*)nullptr, nG, dE, dJ3, dH9, dOk);
     return 0;
 }
@@ -287,7 +368,7 @@ int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, const int32_t* d
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nG == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dAdjTets, dAdjOff,
+    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves()), 256, 0, pick(c, stream), dV, (const int4*)dTets, dAdjTets, dAdjOff,
                (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk);
     return 0;
 }
@@ -299,7 +380,7 @@ int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const i
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nG == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, 16), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
+    TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, ring_waves()), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
                (const int32_t*)nullptr, (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr);
     return 0;
 }

@@ -64,7 +64,7 @@ struct Front {
 };
 
 __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
-                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group) {
+                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
@@ -91,7 +91,18 @@ __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, 
     int sp = 0;
     for (;;) {
         const unsigned need = __ballot_sync(full, !active);
-        if (need) {
+        const unsigned act = ~need;
+        const unsigned pend = __ballot_sync(full, active && pend_mask != 0);
+        const int n_pend = __popc(pend), n_step = __popc(act & ~pend);
+        const bool can_refill = need != 0 && (cb < ce || more);
+        if (act == 0 && !can_refill) break;
+        // Round scheduling: every round the warp runs ONE of three phases -- start queries on idle lanes (scan of the group's
+        // frontier), leaf tests of parked lanes, or a traversal step of the rest -- and the lanes of the other two wait.
+        // policy 1 picks the phase with the most lanes ready (a start scan is ~500 instructions: running it for one or two
+        // lanes at a time is the costliest divergence of this kernel); policy 0 starts queries as soon as a lane is idle.
+        const int n_need = can_refill ? __popc(need) : 0;
+        const bool do_refill = n_need > 0 && (policy == 0 || act == 0 || (n_need >= n_pend && n_need >= n_step));
+        if (do_refill) {
             if (cb >= ce && more) {
                 unsigned long long c = 0;
                 if (lane == 0) c = atomicAdd(counter, 1ull);
@@ -192,14 +203,9 @@ __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, 
                 const uint64_t adv = cb + __popc(need);
                 cb = adv < ce ? adv : ce;
             }
-        }
-        const unsigned act = __ballot_sync(full, active);
-        if (act == 0) {
-            if (!more) break;
             continue;
         }
-        const unsigned pend = __ballot_sync(full, active && pend_mask != 0);
-        if (__popc(pend) >= kLeafQuorum || pend == act) {
+        if (policy == 0 ? (n_pend >= kLeafQuorum || pend == act) : (n_pend >= kLeafQuorum || n_pend >= n_step)) {
             if (active && pend_mask != 0) {
                 const int c = __ffs(pend_mask) - 1;
                 pend_mask &= pend_mask - 1;
@@ -415,8 +421,9 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
     // queries per cooperative group (tuning aid; 64 measured best on C2)
     static const int group = [] { const char* e = getenv("TWG_ENV_GROUP"); int v = e ? atoi(e) : 64; return v < 32 ? 32 : (v > 4096 ? 4096 : v); }();
+    static const int policy = [] { const char* e = getenv("TWG_ENV_POLICY"); return e ? atoi(e) : 1; }();
     TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2,
-               dOut, s->counters + lane, group);
+               dOut, s->counters + lane, group, policy);
     if (trace) fprintf(stderr, "[twg] launched\n");
     return 0;
 }

@@ -29,6 +29,31 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, double a, double
     if (s == 123.456) out[0] = s;  // never true for the chosen a, b: keeps the chain alive without a store
 }
 
+// The same chain with THREE DISTINCT register operands per DFMA (a[k], b[k] live in registers, loaded from memory so that
+// they cannot be folded): what real FP64 code (cross products, dot products) looks like to the register file. If this
+// variant is slower than dfma_kernel, the gap is operand bandwidth, and it is the ceiling a kernel like winding_kernel
+// (FP64 pipe ~67 % active with math_pipe_throttle stalls) actually runs against.
+__global__ void __launch_bounds__(256) dfma3_kernel(double* out, const double* __restrict__ coef, int outer) {
+    double x[kChains], a[kChains], b[kChains];
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) {
+        x[k] = (double)(threadIdx.x + k) * 1e-3;
+        a[k] = coef[k] - 1e-12 * threadIdx.x;           // per-thread values: vector registers, not uniform ones
+        b[k] = coef[kChains + k] + 1e-12 * threadIdx.x;
+    }
+    for (int o = 0; o < outer; ++o) {
+#pragma unroll 16
+        for (int i = 0; i < kInner; ++i) {
+#pragma unroll
+            for (int k = 0; k < kChains; ++k) x[k] = __fma_rn(x[k], a[k], b[k]);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChains; ++k) s += x[k];
+    if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, uint64_t n2) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (uint64_t)gridDim.x * blockDim.x) {
         double2 v = ld_stream2(reinterpret_cast<const double*>(src + i));
@@ -61,6 +86,37 @@ int twg_measure_fp64_tflops(twg_ctx* c, double* tflops) {
         const double flops = 2.0 * kChains * kInner * (double)outer * 256.0 * grid;
         const double tf = flops / (ms * 1e-3) / 1e12;
         if (rep > 0 && tf > best) best = tf;  // first launch is the warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return 0;
+}
+
+int twg_measure_fp64_tflops_distinct(twg_ctx* c, double* tflops) {
+    TWG_CHECK(c, c && tflops, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    TWG_TRY(twg_ensure_scratch(c, 0, 4096));
+    cudaStream_t st = c->streams[0];
+    double h[2 * kChains];
+    for (int k = 0; k < kChains; ++k) { h[k] = 0.999999 - 1e-7 * k; h[kChains + k] = 1e-7 * (k + 1); }
+    double* coef = (double*)c->dscratch[0] + 32;
+    TWG_CUDA(c, cudaMemcpyAsync(coef, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1;
+    TWG_CUDA(c, cudaEventCreate(&e0));
+    TWG_CUDA(c, cudaEventCreate(&e1));
+    const unsigned grid = (unsigned)c->sm_count * 8;
+    const int outer = 64;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        TWG_CUDA(c, cudaEventRecord(e0, st));
+        TWG_LAUNCH(c, dfma3_kernel, grid, 256, 0, st, (double*)c->dscratch[0], coef, outer);
+        TWG_CUDA(c, cudaEventRecord(e1, st));
+        TWG_CUDA(c, cudaEventSynchronize(e1));
+        float ms = 0.f;
+        TWG_CUDA(c, cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * kChains * kInner * (double)outer * 256.0 * grid / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

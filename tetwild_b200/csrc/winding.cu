@@ -54,44 +54,47 @@ struct WView {
     uint32_t nF;
 };
 
-// 1/sqrt(x) for x > 0 (finite, normal): hardware seed (2^-22.9) + two Newton steps in FP64 -> < 2 ulp, branch free.
-// (CUDA's sqrt() adds a slow-path call per use; the solid-angle sums only need ~1e-15 relative accuracy.)
-__device__ __forceinline__ double rsqrt_fast(double x) {
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double h = 0.5 * x;
-    y = y * fma(-h * y, y, 1.5);
-    y = y * fma(-h * y, y, 1.5);
-    return y;
-}
+// |v| for the solid-angle terms. Hardware seed y0 ~ 1/sqrt(l2) (MUFU.RSQ64H, relative error < 2^-21) followed by ONE
+// third-order correction: with s = l2*y0 and e = 1 - s*y0 (exact to rounding through the fma), sqrt(l2) =
+// s*(1 + e/2 + 3e^2/8 + O(e^3)); the neglected term is < 2^-63 relative. 5 FP64 instructions after the seed, branch free
+// (CUDA's sqrt() adds a slow-path call per use; two Newton steps on the reciprocal root cost 8).
+// The +1e-300 only matters for a query ON a vertex (length 0): the factor then degenerates to a positive real.
 __device__ __forceinline__ double norm3(double x, double y, double z) {
-    const double l2 = fmax(fma(x, x, fma(y, y, z * z)), 1e-280);  // a query ON a vertex: length ~0, the factor degenerates to a positive real
-    return l2 * rsqrt_fast(l2);
+    const double l2 = fma(x, x, fma(y, y, z * z)) + 1e-300;
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(l2));
+    const double s = l2 * y0;
+    const double e = fma(-s, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    return fma(s * e, p, s);
 }
 
 // Running sum of atan2(y_f, x_f) as arg(z) + 2 pi k, z = prod (x_f + i y_f) (see the header comment).
+// BRANCH FREE: the loop bodies that call mul() must stay straight-line code so that the compiler can interleave the
+// unrolled iterations (the complex product is a serial chain of dependent FP64 operations; everything else of the next
+// point overlaps it). Half planes are told apart by the SIGN BIT of Im z, exactly like atan2 treats signed zeros:
+// U = {sign clear, arg in [+0, pi]}, L = {sign set, arg in [-pi, -0]}. A counter-clockwise factor (sign of y clear,
+// angle in [0, pi]) that takes z from U to L went through the negative real axis (k += 1); a clockwise factor from L to U
+// went through it the other way (k -= 1); U<->L moves in the other pairings cross the POSITIVE axis and change nothing.
+// A sign of Im z that rounding gets "wrong" can only happen next to the negative axis (next to the positive axis both
+// products of zr*y + zi*x have the same sign), where arg + 2 pi k is continuous, so the bookkeeping stays exact.
 struct Angle {
     double zr, zi;
     int k;
     __device__ __forceinline__ void init() { zr = 1.0; zi = 0.0; k = 0; }
-    // exact bookkeeping of the negative-real-axis crossings; only reached when Im z changes sign or is zero
-    static __device__ __noinline__ int cross(double zr, double zi, double nr, double ni, double x, double y) {
-        const bool up_old = zi > 0.0 || (zi == 0.0 && zr < 0.0);  // arg z in (0, pi]
-        const bool up_new = ni > 0.0 || (ni == 0.0 && nr < 0.0);
-        const bool ccw = y > 0.0 || (y == 0.0 && x < 0.0);        // factor angle in (0, pi]
-        return ((ccw && up_old && !up_new) ? 1 : 0)               // crossed counter-clockwise
-               - ((!ccw && !up_old && up_new) ? 1 : 0);           // ... clockwise
-    }
     // z *= (x + i y) * 2^-e, e = the larger binary exponent of x, y (integer pipe); skip = chain start / zero factor
     __device__ __forceinline__ void mul(double x, double y, bool skip) {
-        const int ex = __double2hiint(x) & 0x7ff00000, ey = __double2hiint(y) & 0x7ff00000;
-        const int e = max(ex, ey);
-        if (e == 0 || skip) return;  // x = y = 0 (atan2(0,0) = 0 in the reference) or no triangle here
+        const int e = max(__double2hiint(x) & 0x7ff00000, __double2hiint(y) & 0x7ff00000);
+        skip = skip || e == 0;       // x = y = 0 (atan2(0,0) = 0 in the reference) or no triangle here: multiply by 1
         const double sc = __hiloint2double(0x7fe00000 - e, 0);
         x *= sc; y *= sc;            // |x + i y| in [1, 2 sqrt 2)
-        const double nr = zr * x - zi * y;
-        const double ni = zr * y + zi * x;
-        if (zi * ni <= 0.0) k += cross(zr, zi, nr, ni, x, y);
+        x = skip ? 1.0 : x;
+        y = skip ? 0.0 : y;
+        const double nr = fma(zr, x, -(zi * y));
+        const double ni = fma(zr, y, zi * x);
+        const int hz = __double2hiint(zi), hn = __double2hiint(ni), hy = __double2hiint(y);
+        const int m = (hz ^ hn) & ~(hy ^ hz);  // sign bit: half plane changed AND the factor turns away from the old half plane
+        k += (m >> 31) & (2 * (hz >> 31) + 1);
         zr = nr; zi = ni;
     }
     __device__ __forceinline__ void renorm() {  // after at most 32 factors: |z| < 2^49 -> back to [1, 2 sqrt 2)
@@ -144,7 +147,7 @@ __device__ __forceinline__ void eval_cap(const WView& W, const WNode& nd, double
             const double ab = ax * bx + ay * by + az * bz;
             const double y = ox * (ay * bz - az * by) + oy * (az * bx - ax * bz) + oz * (ax * by - ay * bx);
             const double x = lo * (la * lb + ab) + ob * la + oa * lb;
-            acc.mul(x, y, v.y != 0.0);  // warp-uniform flag: the first point of a chain closes no triangle
+            acc.mul(x, y, __double2hiint(v.y) != 0);  // flag 1.0 (integer test): the first point of a chain closes no triangle
             ax = bx; ay = by; az = bz; la = lb; oa = ob;
         }
         acc.renorm();
@@ -191,7 +194,10 @@ __device__ __forceinline__ void eval_tris(const WView& W, uint32_t off, uint32_t
     }
 }
 
-__global__ void __launch_bounds__(kWThreads) winding_kernel(WView W, const double* __restrict__ Q, const uint32_t* __restrict__ perm, uint64_t n,
+// MINB = resident CTAs per SM the register allocation is capped for: 4 -> 64 registers (32 warps per SM, a few bytes of
+// spill outside the tile loops), 3 -> 76 registers (24 warps). The kernel is bound by FP64 issue latency, not bandwidth.
+template <int MINB>
+__global__ void __launch_bounds__(kWThreads, MINB) winding_kernel(WView W, const double* __restrict__ Q, const uint32_t* __restrict__ perm, uint64_t n,
                                                            double* __restrict__ Wout, uint8_t* __restrict__ keep) {
     __shared__ __align__(128) unsigned char sbuf[kWarps * 2 * kStageBytes];
     __shared__ __align__(8) uint64_t sbar[kWarps * 2];
@@ -599,7 +605,9 @@ int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* 
     if (w->sort_queries && nC > 32) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dC, nC, &perm, w->sort_box));
     const uint64_t ngroups = (nC + 31) / 32;
     unsigned grid = (unsigned)std::min<uint64_t>((ngroups + kWarps - 1) / kWarps, (uint64_t)c->sm_count * 32);
-    TWG_LAUNCH(c, winding_kernel, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
+    static const int minb = [] { const char* e = getenv("TWG_WINDING_MINB"); return e ? atoi(e) : 3; }();
+    if (minb >= 4) TWG_LAUNCH(c, winding_kernel<4>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
+    else TWG_LAUNCH(c, winding_kernel<3>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
     return 0;
 }
 
