@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(time python -m pytest tests/test_gpu_envelope.py tests/test_cpp_adapters.py -m gpu -x -q) > gpurun_out/s8_pytest.log 2>&1
+tail -3 gpurun_out/s8_pytest.log
+python bench.py --parts envelope_faces --steps 3 --warmup 3 > gpurun_out/s8_bench_faces.log 2>&1; python scripts/bench_summary.py gpurun_out/s8_bench_faces.log
+ncu --set full --clock-control none --import-source on -k regex:env_faces -s 1 -c 1 -f -o gpurun_out/s8_faces python scripts/prof_part.py faces 100000 2 > gpurun_out/s8_ncu_faces.log 2>&1
+tail -1 gpurun_out/s8_ncu_faces.log

@@ -121,6 +121,37 @@ def test_faces_out_exact(knot, ctx, oracle):
     assert len(Si.faces_out(np.zeros((0, 9)), 1e-3, 1e-6)) == 0
 
 
+def test_faces_large_and_tiny(ctx, oracle):
+    """Face sizes that drive every path of the face kernel: tiny faces (3 samples, Common.cpp:154-158), faces taller than
+    one pass of the run table (hundreds of lattice rows), faces whose candidate-facet list overflows (per-sample descents),
+    on a planar grid where IN / OUT is known, and against the oracle when tilted."""
+    g = 24
+    x = np.linspace(0, 1, g + 1)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    V = np.stack([X.ravel(), Y.ravel(), 0 * X.ravel()], 1)
+    idx = np.arange((g + 1) * (g + 1)).reshape(g + 1, g + 1)
+    F = np.concatenate([np.stack([idx[:-1, :-1], idx[1:, :-1], idx[1:, 1:]], -1).reshape(-1, 3),
+                        np.stack([idx[:-1, :-1], idx[1:, 1:], idx[:-1, 1:]], -1).reshape(-1, 3)]).astype(np.uint32)
+    S, OS = tw.Surface(ctx, V, F), oracle.Surface(V, F)
+    sd, eps = 1e-3, 5e-4
+    rng = np.random.default_rng(8)
+    faces = []
+    for edge in (3e-4, 0.02, 0.11, 0.45):          # 3 samples / ~300 / ~8 k / ~120 k samples, 1 .. 390 rows
+        for _ in range(6):
+            c = rng.uniform(0.3, 0.7, 2)
+            a = rng.uniform(0, 2 * np.pi) + np.array([0, 2.1, 4.2])
+            t = np.stack([c[0] + edge / 1.7 * np.cos(a), c[1] + edge / 1.7 * np.sin(a), np.zeros(3)], 1)
+            faces.append(t)
+    T = np.array(faces).reshape(-1, 9)
+    assert not S.faces_out(T, sd, eps * eps).any()                     # in the plane: IN, every sample visited
+    Tup = T.copy(); Tup[:, 2::3] += 2 * eps
+    assert S.faces_out(Tup, sd, eps * eps).all()                       # lifted by 2 eps: OUT
+    Ttilt = T.copy(); Ttilt[:, 8] += rng.uniform(0, 4 * eps, len(T))   # one corner lifted: mixed, decided by a few samples
+    got = S.faces_out(Ttilt, sd, eps * eps)
+    ref, ns = OS.faces_out(Ttilt, sd, eps * eps, threads=4)
+    assert np.array_equal(got, ref) and 0 < got.sum() < len(T) and ns.max() > 50000
+
+
 def test_full_size_config2(ctx, oracle):
     """BASELINE config 2 at full size (200 000 triangles, 10 M points): subsample vs the oracle + properties."""
     V, F = synth.torus_knot(1000, 100)

@@ -293,7 +293,105 @@ __device__ __forceinline__ bool sample_out(const SurfaceView& S, tw::V3 p, doubl
     return true;
 }
 
-constexpr int kEdgeChunk = 32;  // edge runs are dealt out in chunks of this many samples
+// Face kernel: one warp per candidate face, the samples of sampleTriangle FLATTENED and dealt out in equal contiguous
+// chunks. The sample set is a list of runs (sampling.cuh): base edge, the two single vertices, the two other edges, and one
+// run per lattice row. The lanes build the run table together (lane j plans row base+j: the row's first sample and its
+// length, with the reference's own int truncations), a warp scan turns the lengths into offsets, and lane l then walks
+// samples [l*c, (l+1)*c) of the concatenation, c = ceil(S / 32): every lane gets the same number of samples whatever the
+// shape of the triangle (rows of a triangle shrink towards the apex; one lane per row left two thirds of the warp idle),
+// and consecutive samples of a lane are neighbours on the face, so the previous facet is the right hint
+// (LocalOperations.cpp:1080-1086). The first OUT sample raises a warp-shared flag and the warp stops; the answer does not
+// depend on the order in which samples are visited (the reference starts from the middle sample only to exit earlier).
+// Candidate facets of one face. Every sample of a face lies in the face's bounding box, so a facet within eps of ANY sample
+// has its (outward-rounded) leaf box inside that box dilated by eps. The warp therefore walks the tree ONCE per face --
+// the same 8-wide cooperative refinement as the point kernel's group frontier, continued down to the leaves: lane j tests
+// candidate box j against the dilated face box, survivors are compacted with a ballot -- and a sample only tests the
+// facets of that list (FP32 lower bound of the box distance first, the exact point-triangle routine for the boxes within
+// eps). One traversal per face instead of one per sample, and the per-sample work is a uniform loop over shared memory.
+// A face too large for a leaf list (more than kCandMax leaves) falls back to per-sample descents from the root with the
+// previous facet as hint (measured: scanning a 96-node frontier per sample costs more than the 18-level descent it saves).
+constexpr int kCandMax = 96;
+struct Cands {
+    uint32_t node[kCandMax];
+    float box[kCandMax][6];
+};
+// returns the number of nodes left in *res: leaves (heap ids >= nLeafP) when *leaves, else the subtree roots of the deepest
+// level that fitted
+__device__ __forceinline__ int collect_leaves(const SurfaceView& S, const float lo[3], const float hi[3], Cands* A, Cands* B, int lane, const Cands** res,
+                                              bool* leaves) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const float inf = __int_as_float(0x7f800000);
+    const int L = 31 - __clz(S.nLeafP);
+    const uint32_t first = 1u << (L % 3);
+    __syncwarp();
+    if ((uint32_t)lane < first) {
+        A->node[lane] = first + lane;  // root-level boxes are not stored: always admitted
+        A->box[lane][0] = A->box[lane][1] = A->box[lane][2] = -inf;
+        A->box[lane][3] = A->box[lane][4] = A->box[lane][5] = inf;
+    }
+    __syncwarp();
+    int count = (int)first;
+    int d = L % 3;
+    for (; d + 3 <= L && count > 0; d += 3) {
+        const int total = 8 * count;
+        int ncount = 0;
+        bool overflow = false;
+        for (int base = 0; base < total; base += 32) {
+            const int idx = base + lane;
+            bool ok = false;
+            uint32_t child = 0;
+            float b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+            if (idx < total) {
+                child = 8u * A->node[idx >> 3] + (uint32_t)(idx & 7);
+                const float* rec = reinterpret_cast<const float*>(S.pairs + (child >> 1)) + 6 * (child & 1u);
+                const float2 u = __ldg(reinterpret_cast<const float2*>(rec));
+                const float2 v = __ldg(reinterpret_cast<const float2*>(rec) + 1);
+                const float2 w = __ldg(reinterpret_cast<const float2*>(rec) + 2);
+                b0 = u.x; b1 = u.y; b2 = v.x; b3 = v.y; b4 = w.x; b5 = w.y;
+                ok = b0 <= hi[0] && b3 >= lo[0] && b1 <= hi[1] && b4 >= lo[1] && b2 <= hi[2] && b5 >= lo[2];
+            }
+            const unsigned m = __ballot_sync(full, ok);
+            if (ncount + __popc(m) > kCandMax) { overflow = true; break; }
+            if (ok) {
+                const int pos = ncount + __popc(m & lt);
+                B->node[pos] = child;
+                B->box[pos][0] = b0; B->box[pos][1] = b1; B->box[pos][2] = b2;
+                B->box[pos][3] = b3; B->box[pos][4] = b4; B->box[pos][5] = b5;
+            }
+            ncount += __popc(m);
+        }
+        __syncwarp();
+        if (overflow) break;  // A still holds the last level that fitted
+        Cands* t = A; A = B; B = t;
+        count = ncount;
+    }
+    *res = A;
+    *leaves = (d == L) || count == 0;
+    return count;
+}
+
+// one sample against the candidate list: hint facet first (LocalOperations.cpp:1080-1086), then the listed facets
+__device__ __forceinline__ bool sample_out_cands(const SurfaceView& S, tw::V3 p, double eps2, float thr, uint32_t& prev, const Cands* C, int ncand) {
+    double s, t; tw::V3 nd; bool deg;
+    if (prev != TWG_NO_FACET && twd::facet_d2(S, prev, p, s, t, nd, deg) <= eps2) return false;
+    const twd::PointF q = twd::bracket(p);
+    for (int i = 0; i < ncand; ++i) {
+        const float d = twd::box_d2_lb(q, C->box[i][0], C->box[i][1], C->box[i][2], C->box[i][3], C->box[i][4], C->box[i][5]);
+        if (d <= thr) {
+            const uint32_t pos = C->node[i] - S.nLeafP;
+            if (pos != prev && pos < S.nF && twd::facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { prev = pos; return false; }
+        }
+    }
+    return true;
+}
+
+constexpr int kRunCap = 128;  // runs per pass: 4 fixed + up to 124 rows; taller triangles take more passes
+struct __align__(16) FaceRun {
+    double ox, oy, oz;  // first sample of a row (rows only)
+    int cnt;            // samples in this run
+    int off;            // samples before this run (exclusive scan)
+};
 
 __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
                                                                uint8_t* __restrict__ out) {
@@ -301,8 +399,14 @@ __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, c
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
     __shared__ volatile int flag[kEnvThreads / 32];
+    __shared__ FaceRun runs_all[kEnvThreads / 32][kRunCap];
+    __shared__ Cands cands_all[kEnvThreads / 32][2];
     const uint32_t topN = stage_top(S, top, &bar);
+    const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    FaceRun* runs = runs_all[wib];
+    const float thr = __double2float_ru(eps2);
+    const float epsf = __fsqrt_ru(thr);
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t f = warp; f < n; f += nwarps) {
@@ -311,6 +415,27 @@ __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, c
         for (int k = 0; k < 9; ++k) t9[k] = __ldg(tris + f * 9 + k);
         if (tw::exact::triangle_is_degenerate(t9, t9 + 3, t9 + 6)) {  // :1048
             if (lane == 0) out[f] = 0;
+            continue;
+        }
+        // ---- candidate facets: leaves meeting the face's bounding box dilated by eps. The samples are convex combinations of
+        // the vertices up to rounding (a few 1e-16 relative); the dilation is widened by 1e-4 eps + 4 float ulps of the
+        // largest coordinate, orders of magnitude more than that.
+        float flo[3], fhi[3];
+        float amax = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double mn = fmin(t9[k], fmin(t9[3 + k], t9[6 + k])), mx = fmax(t9[k], fmax(t9[3 + k], t9[6 + k]));
+            flo[k] = __double2float_rd(mn); fhi[k] = __double2float_ru(mx);
+            amax = fmaxf(amax, fmaxf(fabsf(flo[k]), fabsf(fhi[k])));
+        }
+        const float pad = __fadd_ru(__fmul_ru(epsf, 1.0001f), __fmul_ru(amax, 4.8e-7f));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { flo[k] = __fsub_rd(flo[k], pad); fhi[k] = __fadd_ru(fhi[k], pad); }
+        const Cands* cand = nullptr;
+        bool leaves = false;
+        const int ncand = collect_leaves(S, flo, fhi, &cands_all[wib][0], &cands_all[wib][1], lane, &cand, &leaves);
+        if (ncand == 0) {  // nothing of the surface within eps of the face's box: every sample is out
+            if (lane == 0) out[f] = 1;
             continue;
         }
         tw::SamplePlan P;
@@ -323,7 +448,7 @@ __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, c
                 const int m = base + lane + 1;
                 bool stop = false;
                 if (m <= P.M) { tw::RowPlan R; tw::make_row(P, m, R); stop = R.stop; }
-                const unsigned b = __ballot_sync(0xffffffffu, stop);
+                const unsigned b = __ballot_sync(full, stop);
                 if (b) { rows = base + __ffs(b) - 1; break; }
             }
         }
@@ -331,36 +456,79 @@ __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, c
         __syncwarp();
         uint32_t prev = TWG_NO_FACET;
         bool found_out = false;
-        // work items: [0] single vertices, then edge chunks A, B, C, then rows
-        const int cA = (P.nA + kEdgeChunk - 1) / kEdgeChunk, cB = (P.nB + kEdgeChunk - 1) / kEdgeChunk, cC = (P.nC + kEdgeChunk - 1) / kEdgeChunk;
-        const int items = 1 + cA + cB + cC + rows;
-        for (int it = lane; it < items && !found_out; it += 32) {
+        // passes over the run list: pass 0 holds the four fixed runs + the first rows, later passes the remaining rows
+        for (int row0 = 0; row0 == 0 || row0 < rows; ) {
+            const int fixed = (row0 == 0) ? 4 : 0;
+            const int nrow = min(rows - row0, kRunCap - fixed);
+            const int nrun = fixed + nrow;
+            // ---- run table: lengths
+            if (row0 == 0 && lane < 4) {
+                // run 0: base edge n = 0..nA-1; run 1: the single vertices (kind 0: v0 v1 v2, else v1 and v2);
+                // run 2: edge v1->v2, n = 1..nB; run 3: edge v2->v0, n = 1..nC
+                const int c = (lane == 0) ? P.nA : (lane == 1) ? ((P.kind == 0) ? 3 : 2) : (lane == 2) ? P.nB : P.nC;
+                runs[lane].cnt = c;
+            }
+            for (int base = 0; base < nrow; base += 32) {
+                const int j = base + lane;
+                if (j < nrow) {
+                    tw::RowPlan R;
+                    tw::make_row(P, row0 + j + 1, R);
+                    FaceRun& r = runs[fixed + j];
+                    r.ox = R.v.x; r.oy = R.v.y; r.oz = R.v.z;
+                    r.cnt = R.N1 + 1 > 0 ? R.N1 + 1 : 0;
+                }
+            }
+            __syncwarp();
+            // ---- exclusive scan of the lengths
+            int total = 0;
+            for (int base = 0; base < nrun; base += 32) {
+                const int j = base + lane;
+                const int c = (j < nrun) ? runs[j].cnt : 0;
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(full, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                if (j < nrun) runs[j].off = total + incl - c;
+                total += __shfl_sync(full, incl, 31);
+            }
+            __syncwarp();
+            // ---- every lane walks its chunk of the concatenated runs
+            const int chunk = (total + 31) / 32;
+            int sidx = lane * chunk;
+            const int send = min(total, sidx + chunk);
+            if (sidx < send && !found_out) {
+                int lo = 0, hi = nrun - 1;  // last run with off <= sidx and cnt > 0 covering sidx
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (runs[mid].off <= sidx) lo = mid; else hi = mid - 1;
+                }
+                int r = lo;
+                while (runs[r].cnt == 0 || runs[r].off + runs[r].cnt <= sidx) ++r;  // skip empty runs that share the offset
+                int i = sidx - runs[r].off;
+                for (; sidx < send; ++sidx) {
+                    if (flag[wib]) break;
+                    while (i >= runs[r].cnt) { ++r; i = 0; }
+                    tw::V3 p;
+                    if (r >= fixed) p = tw::row_sample(tw::mk(runs[r].ox, runs[r].oy, runs[r].oz), P.n01, sd, i);
+                    else if (r == 0) p = tw::edge_sample(P.v0, P.n01, sd, i);
+                    else if (r == 1) p = (P.kind == 0) ? (i == 0 ? P.v0 : (i == 1 ? P.v1 : P.v2)) : (i == 0 ? P.v1 : P.v2);
+                    else if (r == 2) p = tw::edge_sample(P.v1, P.n12, sd, i + 1);
+                    else p = tw::edge_sample(P.v2, P.n20, sd, i + 1);
+                    const bool is_out = leaves ? sample_out_cands(S, p, eps2, thr, prev, cand, ncand) : sample_out(S, p, eps2, prev, top, topN);
+                    if (is_out) { found_out = true; flag[wib] = 1; break; }
+                    ++i;
+                }
+            }
+            __syncwarp();
             if (flag[wib]) break;
-            int kind, lo, hi;  // kind 0: the single vertices, 1: edge formula, 2: row formula; multipliers [lo, hi)
-            tw::V3 o = P.v0, dir = P.n01;
-            if (it == 0) {
-                kind = 0; lo = (P.kind == 0) ? 0 : 1; hi = 3;
-            } else if (it < 1 + cA + cB + cC) {
-                int c = it - 1;
-                kind = 1;
-                if (c < cA) { lo = c * kEdgeChunk; hi = min(lo + kEdgeChunk, P.nA); }
-                else if (c < cA + cB) { c -= cA; o = P.v1; dir = P.n12; lo = 1 + c * kEdgeChunk; hi = min(lo + kEdgeChunk, P.nB + 1); }
-                else { c -= cA + cB; o = P.v2; dir = P.n20; lo = 1 + c * kEdgeChunk; hi = min(lo + kEdgeChunk, P.nC + 1); }
-            } else {
-                tw::RowPlan R;
-                tw::make_row(P, it - (1 + cA + cB + cC) + 1, R);
-                kind = 2; o = R.v; lo = 0; hi = R.N1 + 1;
-            }
-            for (int k = lo; k < hi; ++k) {
-                if (flag[wib]) break;
-                const tw::V3 p = (kind == 0) ? (k == 0 ? P.v0 : (k == 1 ? P.v1 : P.v2))
-                                             : (kind == 1 ? tw::edge_sample(o, dir, sd, k) : tw::row_sample(o, dir, sd, k));
-                if (sample_out(S, p, eps2, prev, top, topN)) { found_out = true; break; }
-            }
-            if (found_out) flag[wib] = 1;
+            row0 += nrow;
+            if (nrow == 0) break;
+            __syncwarp();
         }
         __syncwarp();
-        const unsigned any = __ballot_sync(0xffffffffu, found_out);
+        const unsigned any = __ballot_sync(full, found_out);
         if (lane == 0) out[f] = any ? 1 : 0;
         __syncwarp();
     }

@@ -107,12 +107,13 @@ __device__ __forceinline__ float box_d2_lb(const PointF& q, float lx, float ly, 
 // Is some facet within sqrt(eps2) of p?  (facet_in_envelope_recursive, mesh_AABB.cpp:482-548: stop at the first
 // facet with d2 <= eps2, never enter a box farther than eps.)  Binary descent, one query per lane; used by the
 // face kernel, whose lanes each walk their own run of samples. top/topN: pair records [0, topN) staged in shared memory.
-__device__ __forceinline__ bool in_envelope(const SurfaceView& S, tw::V3 p, double eps2, uint32_t& hit_pos, const NodePair* top, uint32_t topN) {
+__device__ __forceinline__ bool in_envelope(const SurfaceView& S, tw::V3 p, double eps2, uint32_t& hit_pos, const NodePair* top, uint32_t topN,
+                                            uint32_t start = 1u) {  // start: root of the subtree to search (an internal node)
     const float thr = __double2float_ru(eps2);
     const PointF q = bracket(p);
     uint32_t stack[32];
     int sp = 0;
-    uint32_t node = 1;
+    uint32_t node = start;
     const uint32_t leaf0 = S.nLeafP;
     for (;;) {
         NodePair np = (node < topN) ? top[node] : load_pair(S.pairs + node);
