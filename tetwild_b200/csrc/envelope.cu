@@ -63,7 +63,8 @@ struct Front {
     float box[kFrontMax][6];
 };
 
-__global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
+template <int MINB>  // resident CTAs per SM the register allocation is capped for (8 -> 64 registers, 32 warps per SM)
+__global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
                                                                 uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
@@ -246,18 +247,29 @@ __global__ void __launch_bounds__(kEnvThreads) env_points_kernel(SurfaceView S, 
     }
 }
 
+constexpr int kNearRun = 8;  // consecutive sorted queries per lane and claim
 __global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm, uint64_t n,
-                                                             uint32_t* __restrict__ facet, double* __restrict__ nearest, double* __restrict__ d2out) {
+                                                             uint32_t* __restrict__ facet, double* __restrict__ nearest, double* __restrict__ d2out,
+                                                             unsigned long long* counter) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
     const uint32_t topN = stage_top(S, top, &bar);
-    // every thread walks a RUN of consecutive Morton-sorted queries and starts each search from the facet nearest to
+    // every lane walks a RUN of consecutive Morton-sorted queries and starts each search from the facet nearest to
     // its previous query (nearest_facet_with_hint, mesh_AABB.h:162-176 / get_nearest_facet_hint :381-416 play the same
     // role): the initial bound is already within a facet or two of the answer, so far queries no longer open every
     // box on the way down. The result is the minimum over all facets either way.
-    const uint64_t run = (n + (uint64_t)gridDim.x * kEnvThreads - 1) / ((uint64_t)gridDim.x * kEnvThreads);
-    const uint64_t b0 = ((uint64_t)blockIdx.x * kEnvThreads + threadIdx.x) * run, e0 = (b0 + run < n) ? b0 + run : n;
+    // Warps claim 32 x kNearRun queries at a time from a global counter: far queries cost 10-100x a near one and come
+    // in spatial clusters of the sorted order, so a static split left most of the machine idle behind a few long runs
+    // (ncu: 13 % warps active).
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+    unsigned long long claim = 0;
+    if (lane == 0) claim = atomicAdd(counter, 1ull);
+    claim = __shfl_sync(0xffffffffu, claim, 0);
+    const uint64_t cb = claim * (uint64_t)(32 * kNearRun);
+    if (cb >= n) break;
+    const uint64_t b0 = cb + (uint64_t)lane * kNearRun, e0 = (b0 + kNearRun < n) ? b0 + kNearRun : n;
     uint32_t hint = TWG_NO_FACET;
     for (uint64_t j = b0; j < e0; ++j) {
         const uint64_t i = perm ? (uint64_t)__ldg(perm + j) : j;
@@ -279,6 +291,7 @@ __global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, con
                 nearest[3 * i] = q.x; nearest[3 * i + 1] = q.y; nearest[3 * i + 2] = q.z;
             }
         }
+    }
     }
 }
 
@@ -590,8 +603,13 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     // queries per cooperative group (tuning aid; 64 measured best on C2)
     static const int group = [] { const char* e = getenv("TWG_ENV_GROUP"); int v = e ? atoi(e) : 64; return v < 32 ? 32 : (v > 4096 ? 4096 : v); }();
     static const int policy = [] { const char* e = getenv("TWG_ENV_POLICY"); return e ? atoi(e) : 1; }();
-    TWG_LAUNCH(c, env_points_kernel, grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2,
-               dOut, s->counters + lane, group, policy);
+    static const int minb = [] { const char* e = getenv("TWG_ENV_MINB"); return e ? atoi(e) : 8; }();
+    if (minb >= 8)
+        TWG_LAUNCH(c, env_points_kernel<8>, grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n,
+                   eps2, dOut, s->counters + lane, group, policy);
+    else
+        TWG_LAUNCH(c, env_points_kernel<6>, grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 6), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n,
+                   eps2, dOut, s->counters + lane, group, policy);
     if (trace) fprintf(stderr, "[twg] launched\n");
     return 0;
 }
@@ -604,7 +622,10 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     cudaStream_t st = pick(c, stream);
     const uint32_t* perm = nullptr;
     if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm, s->sort_box));
-    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, n, kEnvThreads, 8), kEnvThreads, top_smem(s), st, view_of(s), dP, perm, n, dFacet, dNearest, dD2);
+    const int lane = twg_lane_of(c, st);
+    TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
+    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, (n + 32 * kNearRun - 1) / (32 * kNearRun), kEnvThreads / 32, 5), kEnvThreads, top_smem(s), st, view_of(s), dP,
+               perm, n, dFacet, dNearest, dD2, s->counters + lane);
     return 0;
 }
 
