@@ -29,20 +29,23 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-FULL = {"envelope": 10_000_000, "amips": 50_000_000, "amips_ring": 50_000_000, "winding": 100_000_000, "envelope_faces": 400_000}
-UNIT = {"envelope": "points/s", "amips": "tets/s", "amips_ring": "tets/s", "winding": "queries/s", "envelope_faces": "faces/s"}
+FULL = {"envelope": 10_000_000, "amips": 50_000_000, "amips_ring": 50_000_000, "winding": 100_000_000, "envelope_faces": 400_000, "nearest": 10_000_000, "amips_quality": 50_000_000}
+UNIT = {"envelope": "points/s", "amips": "tets/s", "amips_ring": "tets/s", "winding": "queries/s", "envelope_faces": "faces/s", "nearest": "points/s", "amips_quality": "tets/s"}
 METRIC = {"envelope": "envelope points/s", "amips": "AMIPS E+J+H tet-evals/s", "amips_ring": "AMIPS one-ring E+J+H tet-evals/s",
-          "winding": "winding-number queries/s", "envelope_faces": "envelope faces/s (isFaceOutEnvelop)"}
+          "winding": "winding-number queries/s", "envelope_faces": "envelope faces/s (isFaceOutEnvelop)", "nearest": "nearest-facet projections/s", "amips_quality": "AMIPS tet-quality evals/s (calTetQualities)"}
 FACE_EDGE = 0.02  # C1-shaped candidate faces: small enough that the flat face stays within eps of the curved icosphere about half the time
 WORKLOAD = {
     "envelope": "C2: %d sampled points vs 200000-triangle (2,3) torus knot, eps_rel=1e-3 -> eps_2=(0.42265e-3)^2 (State.cpp:36-41)",
     "amips": "C3: %d random non-degenerate tets, flat SoA (12 arrays), E+J[3]+H[9] per tet, FP64",
     "amips_ring": "C3 smoothing-candidate layout: %d random non-degenerate tets in one-rings of k~U{12..36} around a centre vertex (indexed gather, centre rotated to slot 0), E+J[3]+H[9] per ring (NewtonsUpdate), FP64",
     "winding": "C4: %d centroids uniform in 1.2x bbox vs 1001112-triangle closed noisy UV sphere, keep = W > 0.5",
+    "amips_quality": "C3 indexed layout: calTetQualities over %d random non-degenerate tets (int4 tet -> 4 gathered vertices, exact orientation gate, energy, MAX_ENERGY rules of LocalOperations.cpp:862-884) on the resident tet mesh, FP64",
+    "nearest": "C2 points, full nearest search: %d points vs 200000-triangle torus knot -> nearest facet id + nearest point + d2 (nearest_facet, mesh_AABB.h:130-176; the projection callers VertexSmoother.cpp:354-362, Preprocess.cpp:529)",
     "envelope_faces": "C1-shaped call stream: %d candidate faces (edge ~ diag/50, sampled on the device at sampling_dist = 1e-3 diag like Common.cpp:143-255) vs the 20480-triangle icosphere, eps through State.cpp:36-41",
 }
-# algorithmic HBM bytes per unit (ring: 16 B indices + 72 B gathered vertices + 128 B of per-ring data / 24)
-ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "amips_ring": 93.0, "winding": 25.0, "envelope_faces": 73.0}
+# algorithmic HBM bytes per unit (ring: 16 B indices + 72 B gathered vertices + 128 B of per-ring data / 24;
+# quality: 16 B tet + 96 B gathered vertices + 8 B out)
+ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "amips_ring": 93.0, "winding": 25.0, "envelope_faces": 73.0, "nearest": 60.0, "amips_quality": 120.0}
 
 
 def peaks():
@@ -245,6 +248,13 @@ def cpu_rate(part, n_full, threads, budget_s=8.0):
         T = synth.random_tets(m, seed=7)
         t = time.perf_counter(); fn(T); dt = time.perf_counter() - t
         return m / dt, kind, "%d of %d tets, %s, OpenMP over tets" % (m, n_full, what)
+    if part == "amips_quality":
+        m = int(min(n_full, 4_000_000))
+        V, tets, off, cen = synth.ring_groups(max(1, m // 24), seed=7, scale_lo=0.1, scale_hi=10.0)
+        O.amips_quality(V, tets[:20000], threads=threads)
+        t = time.perf_counter(); O.amips_quality(V, tets, threads=threads); dt = time.perf_counter() - t
+        return len(tets) / dt, "port", ("%d of %d tets, oracle port of calTetQuality_AMIPS (exact orientation predicate + the energy of "
+                                        "LocalOperations.cpp:28-81), OpenMP over tets" % (len(tets), n_full))
     if part == "amips_ring":
         # NewtonsUpdate over one-rings (VertexSmoother.cpp:627-702): per member tet the reference's own E, J, H text
         m = int(min(n_full, 4_000_000))
@@ -256,6 +266,23 @@ def cpu_rate(part, n_full, threads, budget_s=8.0):
         t = time.perf_counter(); fn(V, tets, off, cen, threads=threads); dt = time.perf_counter() - t
         what = "NewtonsUpdate restated around the reference's own LocalOperations.cpp:28-291 E/J/H text (oracle/ref_wrap.cpp)" if have_ref else "oracle port of NewtonsUpdate"
         return nt / dt, kind, "%d of %d tets in %d one-rings, %s, OpenMP over rings" % (nt, n_full, len(cen), what)
+    if part == "nearest":
+        V, F = knot_surface()
+        sd, eps, eps2 = synth.state_eps(1e-3)
+        S = O.Surface(V, F)
+        if have_ref:
+            RT = O.RefTree(V, F[S.order()])
+            fn = lambda P: RT.nearest(P, threads=threads)  # noqa: E731
+            kind, what = "reference", "reference mesh_AABB.cpp nearest_facet (compiled unmodified; geogram leaf distance restated)"
+        else:
+            fn = lambda P: S.nearest(P, threads=threads)  # noqa: E731
+            kind, what = "port", "oracle port of mesh_AABB.cpp:418-480"
+        P = envelope_points_fast(V, F, 50_000, eps, seed=99)
+        t = time.perf_counter(); fn(P); r0 = len(P) / (time.perf_counter() - t)
+        m = int(min(n_full, max(50_000, r0 * budget_s)))
+        P = envelope_points_fast(V, F, m, eps, seed=20240501)
+        t = time.perf_counter(); fn(P); dt = time.perf_counter() - t
+        return m / dt, kind, "%d of %d points, %s, OpenMP over queries" % (m, n_full, what)
     if part == "envelope_faces":
         V, F = synth.icosphere(5)
         V = synth.normalise_unit_diag(V)
@@ -415,6 +442,27 @@ def run_gpu(args, parts):
                                                            "surface_triangles": int(len(F))}})
             res["config"]["l2"] = "inputs larger than L2: 240 MB of points streamed per step; the 38 MB surface structure is meant to stay L2-resident"
             del dP, dO, S
+        elif part == "nearest":
+            V, F = knot_surface()
+            sd, eps, eps2 = synth.state_eps(1e-3)
+            S = tw.Surface(ctx, V, F)
+            P = envelope_points_fast(V, F, n, eps, seed=20240501 + rank)
+            hP = torch.from_numpy(P).pin_memory()
+            dP = hP.to(dev, non_blocking=True)
+            dF = torch.empty(n, device=dev, dtype=torch.int32)
+            dN = torch.empty((n, 3), device=dev, dtype=torch.float64)
+            dD = torch.empty(n, device=dev, dtype=torch.float64)
+            step = lambda: S.nearest_dev(dP.data_ptr(), n, dF.data_ptr(), dN.data_ptr(), dD.data_ptr(), sh)  # noqa: E731
+            ms, kms, launches, win = timed(step)
+            e2e_s = e2e_timed(lambda: S.nearest(hP.numpy()))
+            mism = None
+            if rank == 0:
+                idx = np.random.default_rng(5).choice(n, min(n, 20_000), replace=False)
+                dref = O.Surface(V, F).sqdist_brute(P[idx], threads=O.max_threads())[0]
+                mism = int((dD.cpu().numpy()[idx] != dref).sum())
+            res.update({"h2d": n * 24, "d2h": n * 36, "extra": {"d2_mismatches_vs_brute_force_20k_sample": mism, "surface_triangles": int(len(F))}})
+            res["config"]["l2"] = "inputs larger than L2: 240 MB of points in, 360 MB of results out per step"
+            del dP, dF, dN, dD, S
         elif part == "envelope_faces":
             V, F = synth.icosphere(5)
             V = synth.normalise_unit_diag(V)
@@ -468,6 +516,32 @@ def run_gpu(args, parts):
             res.update({"h2d": n * 96, "d2h": n * 104, "extra": {"parity_vs_reference_text": mism}})
             res["config"]["l2"] = "inputs larger than L2: 4.8 GB read + 5.2 GB written per step"
             del dT, dE, dJ, dH, hT, hE, hJ, hH
+        elif part == "amips_quality":
+            dV, dT4, dOff, dCen = rings_on_device(n, 7 + rank, dev)
+            hV, hT4 = dV.cpu().pin_memory(), dT4.cpu().pin_memory()
+            nV = int(dV.shape[0])
+            del dV, dT4, dOff, dCen
+            torch.cuda.empty_cache()
+            M = tw.TetMesh(ctx, hV.numpy(), hT4.numpy())
+            dQ = torch.empty(n, device=dev, dtype=torch.float64)
+            step = lambda: M.quality_dev(0, n, dQ.data_ptr(), sh)  # noqa: E731
+            ms, kms, launches, win = timed(step)
+            e2e_s = e2e_timed(lambda: M.quality())
+            mism = None
+            if rank == 0:
+                idx = np.random.default_rng(5).choice(n, min(n, 50_000), replace=False)
+                sub = hT4.numpy()[idx]
+                uniq, inv = np.unique(sub.ravel(), return_inverse=True)
+                ref = O.amips_quality(hV.numpy()[uniq], inv.reshape(-1, 4).astype(np.int32), threads=O.max_threads())
+                got = dQ.cpu().numpy()[idx]
+                gate = int(((got == tw.MAX_ENERGY) != (ref == O.MAX_ENERGY)).sum())
+                ok = ref != O.MAX_ENERGY
+                mism = {"gate_mismatches": gate, "max_rel_err": float((np.abs(got[ok] - ref[ok]) / ref[ok]).max()), "sample": int(len(idx))}
+            res.update({"h2d": 0, "d2h": n * 8, "extra": {"vertices": nV, "parity_vs_oracle": mism,
+                                                           "e2e_path": "twg_mesh_quality over every slot of the resident mesh (nothing in, 8 B per tet out)"}})
+            res["config"]["l2"] = "inputs larger than L2: %.1f GB of vertices + %.1f GB of tets gathered per step" % (nV * 24 / 1e9, n * 16 / 1e9)
+            M.close()
+            del dQ, hV, hT4
         elif part == "amips_ring":
             dV, dT4, dOff, dCen = rings_on_device(n, 7 + rank, dev)
             nG, nV = int(dCen.numel()), int(dV.shape[0])
@@ -596,7 +670,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--parts", default="envelope,envelope_faces,amips,amips_ring,winding")
+    ap.add_argument("--parts", default="envelope,envelope_faces,nearest,amips,amips_quality,amips_ring,winding")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the full BASELINE.json batch sizes (1.0 = as named)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-budget", type=float, default=8.0)

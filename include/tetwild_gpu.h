@@ -72,6 +72,14 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
 int twg_envelope_faces_out(twg_surface* s, const double* tris, uint64_t n, double sampling_dist, double eps2, uint8_t* out);
 int twg_envelope_faces_out_dev(twg_surface* s, const double* dTris, uint64_t n, double sampling_dist, double eps2,
                                uint8_t* dOut, void* stream);
+/* flags for the _ex variants */
+#define TWG_FACES_NO_DEGENERATE_SHORTCUT 1u /* sample degenerate faces too, like Preprocess::isOutEnvelop (Preprocess.cpp:643-747) */
+/* the per-face body of Preprocess::isOutEnvelop when flags has TWG_FACES_NO_DEGENERATE_SHORTCUT (the caller ORs the faces of
+ * one candidate set; its eps_2 is the 0.8-scaled one of Preprocess.cpp:201-205); flags = 0 is twg_envelope_faces_out */
+int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, double sampling_dist, double eps2, uint32_t flags,
+                              uint8_t* out);
+int twg_envelope_faces_out_ex_dev(twg_surface* s, const double* dTris, uint64_t n, double sampling_dist, double eps2, uint32_t flags,
+                                  uint8_t* dOut, void* stream);
 
 /* a13: nearest_facet / squared_distance (mesh_AABB.h:130-141,221-226). Any output pointer may be NULL.
  * facet ids are unique up to exact distance ties. */

@@ -156,6 +156,17 @@ public:
     void faces_out_of_envelope(const double* tris, uint64_t n, double sampling_dist, double sq_epsilon, uint8_t* out) const {
         ctx_.check(twg_envelope_faces_out(s_, tris, n, sampling_dist, sq_epsilon, out));
     }
+    /* Preprocess::isOutEnvelop(new_f_ids, geo_sf_mesh, geo_face_tree) (Preprocess.cpp:643-747): true iff ANY face of the set
+     * has a sample farther than eps; unlike isFaceOutEnvelop degenerate faces are sampled too. tris = n*9 doubles (the
+     * V_in / F_in rows of new_f_ids); sq_epsilon is the 0.8-scaled eps_2 Preprocess runs with (:201-205). */
+    bool isOutEnvelop(const double* tris, uint64_t n, double sampling_dist, double sq_epsilon) const {
+        if (n == 0) return false;
+        std::vector<uint8_t> out(n);
+        ctx_.check(twg_envelope_faces_out_ex(s_, tris, n, sampling_dist, sq_epsilon, TWG_FACES_NO_DEGENERATE_SHORTCUT, out.data()));
+        for (uint64_t i = 0; i < n; ++i)
+            if (out[i]) return true;
+        return false;
+    }
     uint32_t nb_facets() const { return twg_surface_num_facets(s_); }
     twg_surface* handle() const { return s_; }
     Context& context() const { return ctx_; }

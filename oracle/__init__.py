@@ -233,12 +233,14 @@ class Surface:
         fn(self.h, _p(P, _dp), C.c_uint64(n), C.c_double(eps2), _p(out, _u8p), C.c_int(threads))
         return out
 
-    def faces_out(self, tris, sampling_dist, eps2, threads=1):
+    def faces_out(self, tris, sampling_dist, eps2, threads=1, degenerate_shortcut=True):
+        """degenerate_shortcut=True: isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109); False: the per-face body of
+        Preprocess::isOutEnvelop (Preprocess.cpp:652-739)"""
         T = _f64(tris).reshape(-1, 9)
         n = len(T)
         out, ns = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint64)
-        lib().ora_envelope_faces_out(self.h, _p(T, _dp), C.c_uint64(n), C.c_double(sampling_dist), C.c_double(eps2),
-                                     _p(out, _u8p), _p(ns, _u64p), C.c_int(threads))
+        lib().ora_envelope_faces_out_ex(self.h, _p(T, _dp), C.c_uint64(n), C.c_double(sampling_dist), C.c_double(eps2),
+                                        C.c_int(1 if degenerate_shortcut else 0), _p(out, _u8p), _p(ns, _u64p), C.c_int(threads))
         return out, ns
 
 

@@ -532,8 +532,9 @@ uint64_t ora_sample_triangle(const double *tri9, double sd, double *samples, uin
 
 /* isFaceOutEnvelop_sampling: LocalOperations.cpp:1046-1109 */
 static int face_out(const ora_surface *s, const double *tri9, double sd, double eps2, double **scratch, uint64_t *cap,
-                    uint64_t *nsamp) {
-    if (ora_triangle_is_degenerate(tri9, tri9 + 3, tri9 + 6)) { if (nsamp) *nsamp = 0; return 0; } /* :1048 */
+                    uint64_t *nsamp, int degenerate_shortcut) {
+    /* :1048; Preprocess::isOutEnvelop (Preprocess.cpp:643-747) samples every face, degenerate or not */
+    if (degenerate_shortcut && ora_triangle_is_degenerate(tri9, tri9 + 3, tri9 + 6)) { if (nsamp) *nsamp = 0; return 0; }
     uint64_t n = ora_sample_triangle(tri9, sd, *scratch, *cap);
     if (n > *cap) {
         *cap = n + n / 2;
@@ -558,6 +559,13 @@ static int face_out(const ora_surface *s, const double *tri9, double sd, double 
 
 void ora_envelope_faces_out(const ora_surface *s, const double *tris9, uint64_t n, double sd, double eps2, uint8_t *out,
                             uint64_t *num_samples, int threads) {
+    ora_envelope_faces_out_ex(s, tris9, n, sd, eps2, 1, out, num_samples, threads);
+}
+
+/* degenerate_shortcut = 1: LocalOperations::isFaceOutEnvelop_sampling (:1046-1109); 0: the per-face body of
+ * Preprocess::isOutEnvelop (Preprocess.cpp:652-739), which has no such shortcut (the caller ORs the faces of a set) */
+void ora_envelope_faces_out_ex(const ora_surface *s, const double *tris9, uint64_t n, double sd, double eps2,
+                               int degenerate_shortcut, uint8_t *out, uint64_t *num_samples, int threads) {
     (void)threads;
 #pragma omp parallel num_threads(threads > 0 ? threads : 1)
     {
@@ -566,7 +574,7 @@ void ora_envelope_faces_out(const ora_surface *s, const double *tris9, uint64_t 
 #pragma omp for schedule(dynamic, 16)
         for (int64_t i = 0; i < (int64_t)n; ++i) {
             uint64_t ns = 0;
-            out[i] = (uint8_t)face_out(s, tris9 + 9 * i, sd, eps2, &scratch, &cap, &ns);
+            out[i] = (uint8_t)face_out(s, tris9 + 9 * i, sd, eps2, &scratch, &cap, &ns, degenerate_shortcut);
             if (num_samples) num_samples[i] = ns;
         }
         free(scratch);

@@ -70,6 +70,9 @@ uint64_t ora_sample_triangle(const double *tri9, double sampling_dist, double *s
 void ora_envelope_faces_out(const ora_surface *s, const double *tris9, uint64_t n, double sampling_dist, double eps2,
                             uint8_t *out, uint64_t *num_samples, int threads);
 
+void ora_envelope_faces_out_ex(const ora_surface *s, const double *tris9, uint64_t n, double sampling_dist, double eps2,
+                               int degenerate_shortcut, uint8_t *out, uint64_t *num_samples, int threads);
+
 /* ---- winding number (winding.c) ---- */
 double ora_solid_angle_w(const double *a, const double *b, const double *c, const double *p);
 void ora_winding_direct(const double *V, uint32_t nV, const uint32_t *F, uint32_t nF, const double *C, uint64_t nC,

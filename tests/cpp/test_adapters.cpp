@@ -170,6 +170,24 @@ int main() {
         f_out += o;
     }
     EXPECT(f_out > 10 && f_out < 390, "degenerate test: %d of 400 faces out", f_out);
+    // Preprocess::isOutEnvelop (Preprocess.cpp:643-747): sets of faces, no degenerate shortcut, eps scaled by 0.8
+    {
+        const double eps2p = ep.eps_2 * 0.8 * 0.8;
+        int n_true = 0;
+        for (size_t b = 0; b + 8 <= tris.size(); b += 8) {
+            double t9[8 * 9];
+            for (int f = 0; f < 8; ++f)
+                for (int k = 0; k < 3; ++k)
+                    for (int a = 0; a < 3; ++a) t9[9 * f + 3 * k + a] = tris[b + f][k][a];
+            uint8_t o[8];
+            ora_envelope_faces_out_ex(osf, t9, 8, ep.sampling_dist, eps2p, 0, o, nullptr, 1);
+            bool any = false;
+            for (int f = 0; f < 8; ++f) any = any || o[f];
+            EXPECT(geo_sf_tree.isOutEnvelop(t9, 8, ep.sampling_dist, eps2p) == any, "Preprocess isOutEnvelop differs at set %zu", b / 8);
+            n_true += any;
+        }
+        EXPECT(n_true > 2 && n_true < 50, "degenerate test: %d of 50 face sets out", n_true);
+    }
 
     // ---------------- AMIPS: calTetQualities, NewtonsUpdate, getNewEnergy, energy_ispc ----------------
     const int nV = 3000;

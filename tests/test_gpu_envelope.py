@@ -121,6 +121,28 @@ def test_faces_out_exact(knot, ctx, oracle):
     assert len(Si.faces_out(np.zeros((0, 9)), 1e-3, 1e-6)) == 0
 
 
+def test_preprocess_face_test_has_no_degenerate_shortcut(knot, oracle):
+    """Preprocess::isOutEnvelop (Preprocess.cpp:643-747) samples every face of the candidate set, degenerate or not;
+    LocalOperations::isFaceOutEnvelop_sampling returns IN for a degenerate face (:1048)."""
+    V, F, S, OS = knot
+    sd, eps, eps2 = synth.state_eps(1e-3)
+    eps2 *= 0.8 * 0.8                                  # Preprocess.cpp:201-205
+    rng = np.random.default_rng(12)
+    T = synth.face_queries(V, F, 800, 0.006, eps, seed=77)
+    # exactly collinear faces: vertices on a 2^-20 grid, third vertex = a + k d with k in {1/2, 2, 3} (exact in double)
+    a = np.round(T[::5, 0:3] * 2 ** 20) / 2 ** 20
+    d = np.round((T[::5, 3:6] - a) * 2 ** 19) / 2 ** 19
+    T[::5, 0:3], T[::5, 3:6] = a, a + d
+    T[::5, 6:9] = a + d * rng.choice([0.5, 2.0, 3.0], (len(a), 1))
+    T[3::50, 3:6] = T[3::50, 0:3]; T[3::50, 6:9] = T[3::50, 0:3]      # three coincident vertices
+    got = S.faces_out(T, sd, eps2, degenerate_shortcut=False)
+    ref, _ = OS.faces_out(T, sd, eps2, threads=4, degenerate_shortcut=False)
+    assert np.array_equal(got, ref)
+    short = S.faces_out(T, sd, eps2)
+    assert not short[::5].any() and got[::5].any()                    # the shortcut hides OUT degenerate faces
+    assert np.array_equal(short, OS.faces_out(T, sd, eps2, threads=4)[0])
+
+
 def test_faces_large_and_tiny(ctx, oracle):
     """Face sizes that drive every path of the face kernel: tiny faces (3 samples, Common.cpp:154-158), faces taller than
     one pass of the run table (hundreds of lattice rows), faces whose candidate-facet list overflows (per-sample descents),

@@ -270,11 +270,13 @@ class Surface:
     def points_out_dev(self, dP, n, eps2, dOut, stream=0):
         self.ctx._check(self._L.twg_envelope_points_out_dev(self.h, _dev(dP), C.c_uint64(n), C.c_double(eps2), _dev(dOut), _dev(stream)))
 
-    def faces_out(self, tris, sampling_dist, eps2):
-        """out[i] = isFaceOutEnvelop(tris[i]) (LocalOperations.cpp:967-976, :1046-1109)"""
+    def faces_out(self, tris, sampling_dist, eps2, degenerate_shortcut=True):
+        """out[i] = isFaceOutEnvelop(tris[i]) (LocalOperations.cpp:967-976, :1046-1109); degenerate_shortcut=False: the
+        per-face body of Preprocess::isOutEnvelop (Preprocess.cpp:643-747), which samples degenerate faces too"""
         T = _f64(tris).reshape(-1, 9)
         out = np.empty(len(T), dtype=np.uint8)
-        self.ctx._check(self._L.twg_envelope_faces_out(self.h, _ptr(T), C.c_uint64(len(T)), C.c_double(sampling_dist), C.c_double(eps2), _ptr(out)))
+        self.ctx._check(self._L.twg_envelope_faces_out_ex(self.h, _ptr(T), C.c_uint64(len(T)), C.c_double(sampling_dist), C.c_double(eps2),
+                                                          C.c_uint32(0 if degenerate_shortcut else 1), _ptr(out)))
         return out
 
     def faces_out_dev(self, dTris, n, sampling_dist, eps2, dOut, stream=0):

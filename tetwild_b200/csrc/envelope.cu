@@ -407,7 +407,7 @@ struct __align__(16) FaceRun {
 };
 
 __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
-                                                               uint8_t* __restrict__ out) {
+                                                               uint32_t flags, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
@@ -426,7 +426,8 @@ __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, c
         double t9[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) t9[k] = __ldg(tris + f * 9 + k);
-        if (tw::exact::triangle_is_degenerate(t9, t9 + 3, t9 + 6)) {  // :1048
+        // :1048 -- Preprocess::isOutEnvelop (Preprocess.cpp:643-747) has no such shortcut
+        if (!(flags & TWG_FACES_NO_DEGENERATE_SHORTCUT) && tw::exact::triangle_is_degenerate(t9, t9 + 3, t9 + 6)) {
             if (lane == 0) out[f] = 0;
             continue;
         }
@@ -630,12 +631,16 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
 }
 
 int twg_envelope_faces_out_dev(twg_surface* s, const double* dTris, uint64_t n, double sd, double eps2, uint8_t* dOut, void* stream) {
+    return twg_envelope_faces_out_ex_dev(s, dTris, n, sd, eps2, 0u, dOut, stream);
+}
+
+int twg_envelope_faces_out_ex_dev(twg_surface* s, const double* dTris, uint64_t n, double sd, double eps2, uint32_t flags, uint8_t* dOut, void* stream) {
     twg_ctx* c = s ? s->ctx : nullptr;
     TWG_CHECK(c, s && dTris && dOut, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, eps2 >= 0.0 && sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need eps2 >= 0 and finite sampling_dist > 0");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, env_faces_kernel, grid_persistent(c, n, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), pick(c, stream), view_of(s), dTris, n, sd, eps2, dOut);
+    TWG_LAUNCH(c, env_faces_kernel, grid_persistent(c, n, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), pick(c, stream), view_of(s), dTris, n, sd, eps2, flags, dOut);
     return 0;
 }
 
@@ -690,6 +695,10 @@ int twg_nearest(twg_surface* s, const double* P, uint64_t n, uint32_t* facet, do
 }
 
 int twg_envelope_faces_out(twg_surface* s, const double* tris, uint64_t n, double sd, double eps2, uint8_t* out) {
+    return twg_envelope_faces_out_ex(s, tris, n, sd, eps2, 0u, out);
+}
+
+int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, double sd, double eps2, uint32_t flags, uint8_t* out) {
     twg_ctx* c = s ? s->ctx : nullptr;
     TWG_CHECK(c, s && tris && out, TWG_ERR_INVALID_ARG, "null argument");
     if (n == 0) return 0;
@@ -699,7 +708,7 @@ int twg_envelope_faces_out(twg_surface* s, const double* tris, uint64_t n, doubl
     char* base = (char*)c->dscratch[0];
     cudaStream_t st = c->streams[0];
     TWG_CUDA(c, cudaMemcpyAsync(base, tris, n * 72, cudaMemcpyHostToDevice, st));
-    TWG_TRY(twg_envelope_faces_out_dev(s, (const double*)base, n, sd, eps2, (uint8_t*)(base + up(n * 72)), st));
+    TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)base, n, sd, eps2, flags, (uint8_t*)(base + up(n * 72)), st));
     TWG_CUDA(c, cudaMemcpyAsync(out, base + up(n * 72), n, cudaMemcpyDeviceToHost, st));
     TWG_CUDA(c, cudaStreamSynchronize(st));
     return 0;
