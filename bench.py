@@ -454,7 +454,9 @@ def run_gpu(args, parts):
             dD = torch.empty(n, device=dev, dtype=torch.float64)
             step = lambda: S.nearest_dev(dP.data_ptr(), n, dF.data_ptr(), dN.data_ptr(), dD.data_ptr(), sh)  # noqa: E731
             ms, kms, launches, win = timed(step)
-            e2e_s = e2e_timed(lambda: S.nearest(hP.numpy()))
+            hF, hN, hD = torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty((n, 3), dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+            outs = (hF.numpy().view(np.uint32), hN.numpy(), hD.numpy())
+            e2e_s = e2e_timed(lambda: S.nearest(hP.numpy(), out=outs))
             mism = None
             if rank == 0:
                 idx = np.random.default_rng(5).choice(n, min(n, 20_000), replace=False)
@@ -526,7 +528,8 @@ def run_gpu(args, parts):
             dQ = torch.empty(n, device=dev, dtype=torch.float64)
             step = lambda: M.quality_dev(0, n, dQ.data_ptr(), sh)  # noqa: E731
             ms, kms, launches, win = timed(step)
-            e2e_s = e2e_timed(lambda: M.quality())
+            hQ = torch.empty(n, dtype=torch.float64).pin_memory()
+            e2e_s = e2e_timed(lambda: M.quality(out=hQ.numpy()))
             mism = None
             if rank == 0:
                 idx = np.random.default_rng(5).choice(n, min(n, 50_000), replace=False)

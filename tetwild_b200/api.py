@@ -283,11 +283,12 @@ class Surface:
         self.ctx._check(self._L.twg_envelope_faces_out_dev(self.h, _dev(dTris), C.c_uint64(n), C.c_double(sampling_dist), C.c_double(eps2),
                                                            _dev(dOut), _dev(stream)))
 
-    def nearest(self, P):
-        """nearest_facet (mesh_AABB.h:130-141) -> (facet ids in the caller's numbering, nearest points, d2)"""
+    def nearest(self, P, out=None):
+        """nearest_facet (mesh_AABB.h:130-141) -> (facet ids in the caller's numbering, nearest points, d2);
+        `out` = optional preallocated (facet u32[n], nearest f64[n,3], d2 f64[n]) (e.g. pinned)"""
         P = _f64(P)
         n = len(P)
-        f, q, d = np.empty(n, dtype=np.uint32), np.empty((n, 3)), np.empty(n)
+        f, q, d = out if out is not None else (np.empty(n, dtype=np.uint32), np.empty((n, 3)), np.empty(n))
         self.ctx._check(self._L.twg_nearest(self.h, _ptr(P), C.c_uint64(n), _ptr(f), _ptr(q), _ptr(d)))
         return f, q, d
 
@@ -382,10 +383,12 @@ class TetMesh:
         ids = np.ascontiguousarray(t_ids, dtype=np.int32)
         return ids, len(ids)
 
-    def quality(self, t_ids=None):
-        """calTetQuality_AMIPS over the resident mesh (LocalOperations.cpp:862-884); t_ids None = every slot"""
+    def quality(self, t_ids=None, out=None):
+        """calTetQuality_AMIPS over the resident mesh (LocalOperations.cpp:862-884); t_ids None = every slot;
+        `out` = optional preallocated result (e.g. pinned)"""
         ids, n = self._tids(t_ids)
-        out = np.empty(n)
+        if out is None:
+            out = np.empty(n)
         self.ctx._check(self._L.twg_mesh_quality(self.h, _ptr(ids), C.c_uint64(n), _ptr(out)))
         return out
 
