@@ -11,7 +11,8 @@ A step = one pass of one part of the hot path over one synthetic batch:
 `value` = units/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks); `e2e` = the same
 metric through the host-buffer C-ABI call (pinned host inputs, H2D + kernel + D2H inside the timed region).
 N > 1 (torchrun, one rank per GPU): the surface is replicated, every rank processes its own full-size batch
-(weak scaling) and the 1-byte decisions are all-gathered over NCCL inside the timed step.
+(weak scaling) and the 1-byte decisions are all-gathered over NCCL inside the timed region (double-buffered: the gather
+of step k overlaps the kernels of step k+1; the region ends only after the last gather).
 `--impl reference`: the reference's own CPU path (oracle/_ref where the reference compiles here, else the oracle
 port) on all host threads, on a bounded sample of the same workload.
 """
@@ -376,13 +377,49 @@ def run_gpu(args, parts):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(step_fn, gather_fn=None):
+    class Pipe:
+        """Double-buffered 1-byte decisions of one rank + their NCCL all_gather. The gather of step k is issued asynchronously
+        (NCCL's own stream, ordered after step k's kernels) and overlaps the kernels of step k+1, which write the other
+        buffer; a buffer is handed out again only after its previous gather has completed. drain() makes the launching
+        stream wait for every outstanding gather, so the timed region contains all of them."""
+
+        def __init__(self, n):
+            self.buf = [torch.empty(n, device=dev, dtype=torch.uint8) for _ in range(2)]
+            self.gath = [[torch.empty(n, device=dev, dtype=torch.uint8) for _ in range(world)] for _ in range(2)] if world > 1 else None
+            self.work = [None, None]
+            self.k = 0
+
+        def out(self):
+            p = self.k & 1
+            if self.work[p] is not None:
+                self.work[p].wait()
+                self.work[p] = None
+            return self.buf[p]
+
+        def gather(self):
+            p = self.k & 1
+            if world > 1:
+                self.work[p] = dist.all_gather(self.gath[p], self.buf[p], async_op=True)
+            self.k += 1
+
+        def drain(self):
+            for p in range(2):
+                if self.work[p] is not None:
+                    self.work[p].wait()
+                    self.work[p] = None
+
+        def last(self):
+            return self.buf[(self.k - 1) & 1]
+
+    def timed(step_fn, gather_fn=None, drain_fn=None):
         """W warm-up steps, then K steps bracketed by barrier+sync; device time (CUDA events on the launching stream),
         max over ranks. Returns (ms_per_step, kernel_ms_avg, launches, clock window)."""
         for _ in range(Wm):
             step_fn()
             if gather_fn:
                 gather_fn()
+        if drain_fn:
+            drain_fn()
         barrier()
         l0 = ctx.launches
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K + 2)]
@@ -394,6 +431,8 @@ def run_gpu(args, parts):
             ev[3 + 2 * k].record(stream)
             if gather_fn:
                 gather_fn()
+        if drain_fn:
+            drain_fn()
         ev[1].record(stream)
         barrier()
         t1 = time.perf_counter()
@@ -424,11 +463,10 @@ def run_gpu(args, parts):
             P = envelope_points_fast(V, F, n, eps, seed=20240501 + rank)
             hP = torch.from_numpy(P).pin_memory()
             dP = hP.to(dev, non_blocking=True)
-            dO = torch.empty(n, device=dev, dtype=torch.uint8)
-            gath = [torch.empty(n, device=dev, dtype=torch.uint8) for _ in range(world)] if world > 1 else None
-            step = lambda: S.points_out_dev(dP.data_ptr(), n, eps2, dO.data_ptr(), sh)  # noqa: E731
-            gfn = (lambda: dist.all_gather(gath, dO)) if world > 1 else None
-            ms, kms, launches, win = timed(step, gfn)
+            pipe = Pipe(n)
+            step = lambda: S.points_out_dev(dP.data_ptr(), n, eps2, pipe.out().data_ptr(), sh)  # noqa: E731
+            ms, kms, launches, win = timed(step, pipe.gather, pipe.drain)
+            dO = pipe.last()
             hO = torch.empty(n, dtype=torch.uint8).pin_memory()
             e2e_s = e2e_timed(lambda: S.points_out(hP.numpy(), eps2, out=hO.numpy()))
             out_frac = float(dO.float().mean().item())
@@ -441,7 +479,7 @@ def run_gpu(args, parts):
             res.update({"h2d": n * 24, "d2h": n, "extra": {"out_of_envelope_fraction": out_frac, "decision_mismatches_vs_oracle_100k_sample": mism,
                                                            "surface_triangles": int(len(F))}})
             res["config"]["l2"] = "inputs larger than L2: 240 MB of points streamed per step; the 38 MB surface structure is meant to stay L2-resident"
-            del dP, dO, S
+            del dP, dO, S, pipe
         elif part == "nearest":
             V, F = knot_surface()
             sd, eps, eps2 = synth.state_eps(1e-3)
@@ -473,11 +511,10 @@ def run_gpu(args, parts):
             T = synth.face_queries(V, F, n, FACE_EDGE, eps, seed=3 + rank)
             hT = torch.from_numpy(T).pin_memory()
             dTr = hT.to(dev, non_blocking=True)
-            dO = torch.empty(n, device=dev, dtype=torch.uint8)
-            gath = [torch.empty(n, device=dev, dtype=torch.uint8) for _ in range(world)] if world > 1 else None
-            step = lambda: S.faces_out_dev(dTr.data_ptr(), n, sd, eps2, dO.data_ptr(), sh)  # noqa: E731
-            gfn = (lambda: dist.all_gather(gath, dO)) if world > 1 else None
-            ms, kms, launches, win = timed(step, gfn)
+            pipe = Pipe(n)
+            step = lambda: S.faces_out_dev(dTr.data_ptr(), n, sd, eps2, pipe.out().data_ptr(), sh)  # noqa: E731
+            ms, kms, launches, win = timed(step, pipe.gather, pipe.drain)
+            dO = pipe.last()
             e2e_s = e2e_timed(lambda: S.faces_out(hT.numpy(), sd, eps2))
             mism = nsamp = None
             if rank == 0:
@@ -489,7 +526,7 @@ def run_gpu(args, parts):
                                                            "decision_mismatches_vs_oracle_5k_sample": mism,
                                                            "mean_samples_per_face_sampleTriangle": nsamp, "surface_triangles": int(len(F))}})
             res["config"]["l2"] = "L2 flushed by construction: every step re-reads %.0f MB of faces; the 4 MB surface structure stays L2-resident" % (n * 72 / 1e6)
-            del dTr, dO, S
+            del dTr, dO, S, pipe
         elif part == "amips":
             dT = tets_on_device(n, 7 + rank, dev)
             dE = torch.empty(n, device=dev, dtype=torch.float64)
@@ -600,11 +637,10 @@ def run_gpu(args, parts):
             g = torch.Generator(device=dev).manual_seed(11 + rank)
             lo, hi = torch.tensor(V.min(0), device=dev), torch.tensor(V.max(0), device=dev)
             dQ = (0.5 * (lo + hi) + 0.6 * (hi - lo) * (2 * torch.rand((n, 3), generator=g, device=dev, dtype=torch.float64) - 1)).contiguous()
-            dK = torch.empty(n, device=dev, dtype=torch.uint8)
-            gath = [torch.empty(n, device=dev, dtype=torch.uint8) for _ in range(world)] if world > 1 else None
-            step = lambda: Wt.eval_dev(dQ.data_ptr(), n, 0, dK.data_ptr(), sh)  # noqa: E731
-            gfn = (lambda: dist.all_gather(gath, dK)) if world > 1 else None
-            ms, kms, launches, win = timed(step, gfn)
+            pipe = Pipe(n)
+            step = lambda: Wt.eval_dev(dQ.data_ptr(), n, 0, pipe.out().data_ptr(), sh)  # noqa: E731
+            ms, kms, launches, win = timed(step, pipe.gather, pipe.drain)
+            dK = pipe.last()
             hQ = torch.empty((n, 3), dtype=torch.float64).pin_memory()
             hQ.copy_(dQ)
             hK = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -617,7 +653,7 @@ def run_gpu(args, parts):
             res.update({"h2d": n * 24, "d2h": n, "extra": {"inside_fraction": float(dK.float().mean().item()), "hierarchy_build_s": build_s,
                                                            "decision_mismatches_vs_oracle_20k_sample": mism, **Wt.stats()}})
             res["config"]["l2"] = "inputs larger than L2: 2.4 GB of queries per step; the ~210 MB hierarchy is re-read from L2/HBM"
-            del dQ, dK, Wt
+            del dQ, dK, Wt, pipe
         torch.cuda.empty_cache()
         total_units = n * world
         res["value"] = total_units / (ms * 1e-3)
@@ -648,7 +684,7 @@ def run_gpu(args, parts):
                     results[p]["roofline"]["fp64_pipe_active_pct"] = t["fp64_pipe_pct"]
         out = {"metric": h["metric"], "value": h["value"], "unit": h["unit"], "n_gpus": world, "steps": K, "warmup": Wm,
                "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-               "data": "synthetic", "config": dict(h["config"], parallelism="replicated surface, batches split by rank, NCCL all_gather of decisions" if world > 1 else "single GPU"),
+               "data": "synthetic", "config": dict(h["config"], parallelism="replicated surface, batches split by rank, NCCL all_gather of decisions overlapped with the next step's kernels (double-buffered)" if world > 1 else "single GPU"),
                "roofline": h["roofline"], "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "clocks": h["clocks"],
                "cpu_baseline": h.get("cpu_baseline"), "extra": h.get("extra"),
                "parts": {p: results[p] for p in parts if p != head}}
