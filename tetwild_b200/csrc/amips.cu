@@ -102,6 +102,56 @@ __global__ void __launch_bounds__(AM_THREADS) amips_soa_kernel(SoaArgs a) {
     }
 }
 
+// E+J+H for full, 16-byte aligned tiles: the output path is TMA. Thread t evaluates tets t and t+128 of a 256-tet tile
+// (two coalesced 64-bit loads per coordinate array), writes its J rows (3 doubles) and H rows (9 doubles) into shared
+// memory in the FINAL AoS layout -- consecutive lanes are 3 resp. 9 doubles apart, which is conflict-free for 64-bit
+// stores -- and one thread hands the tile's 6 KiB of J and 18 KiB of H to two bulk shared->global copies
+// (cp.async.bulk, UBLKCP in SASS). The copy-out loop of amips_soa_kernel (24 LDS.128 + STG.128 per thread and tile) and
+// one of its two barriers disappear, and the store drains while the next tile is loaded and evaluated: the buffer is
+// only waited for (wait_group.read) right before it is overwritten. The ragged last tile goes through amips_soa_kernel.
+__global__ void __launch_bounds__(AM_THREADS) amips_soa_tma_kernel(SoaArgs a, uint64_t n_tiles) {
+    constexpr int TILE = AM_THREADS * 2;
+    extern __shared__ __align__(128) double sm[];  // [TILE*3] J then [TILE*9] H
+    double* sJ = sm;
+    double* sH = sm + TILE * 3;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t base = tile * TILE;
+        double x[2][12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            x[0][k] = __ldg(a.T[k] + base + threadIdx.x);
+            x[1][k] = __ldg(a.T[k] + base + AM_THREADS + threadIdx.x);
+        }
+        tw::Amips r[2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v) tw::amips_eval<true>(x[v], r[v]);
+        if (a.E) {
+            a.E[base + threadIdx.x] = r[0].E;
+            a.E[base + AM_THREADS + threadIdx.x] = r[1].E;
+        }
+        if (threadIdx.x == 0) tma_store_wait_read();  // the previous tile's bulk stores have read the buffer
+        __syncthreads();
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+            const int row = v * AM_THREADS + threadIdx.x;
+            double* j = sJ + row * 3;
+            j[0] = r[v].J[0]; j[1] = r[v].J[1]; j[2] = r[v].J[2];
+            double* h = sH + row * 9;
+            h[0] = r[v].H[0]; h[1] = r[v].H[1]; h[2] = r[v].H[2];
+            h[3] = r[v].H[1]; h[4] = r[v].H[3]; h[5] = r[v].H[4];
+            h[6] = r[v].H[2]; h[7] = r[v].H[4]; h[8] = r[v].H[5];
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (a.J3) tma_bulk_s2g(a.J3 + base * 3, sJ, TILE * 3 * (uint32_t)sizeof(double));
+            if (a.H9) tma_bulk_s2g(a.H9 + base * 9, sH, TILE * 9 * (uint32_t)sizeof(double));
+            tma_store_commit();
+        }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all();  // global writes complete before the CTA exits
+}
+
 __device__ __forceinline__ void gather_vertex(const double* __restrict__ V, int32_t v, double* dst) {
     const double* p = V + 3 * (size_t)v;
     dst[0] = __ldg(p); dst[1] = __ldg(p + 1); dst[2] = __ldg(p + 2);
@@ -291,6 +341,25 @@ int launch_soa(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, 
     a.E = dE; a.J3 = dJ3; a.H9 = dH9; a.n = n;
     vec = vec && (!dE || aligned16(dE)) && (!dJ3 || aligned16(dJ3)) && (!dH9 || aligned16(dH9));
     const bool jh = (dJ3 != nullptr) || (dH9 != nullptr);
+    static const bool use_tma = [] { const char* e = getenv("TWG_AMIPS_TMA"); return e ? atoi(e) != 0 : true; }();
+    if (vec && jh && use_tma && n >= 2 * AM_THREADS) {
+        // full tiles through the TMA-store kernel, the ragged rest (< 256 tets) through the generic one
+        const uint64_t n_tiles = n / (2 * AM_THREADS);
+        uint64_t blocks = n_tiles;
+        const uint64_t maxb = (uint64_t)c->sm_count * 8;
+        if (blocks > maxb) blocks = maxb;
+        TWG_LAUNCH(c, amips_soa_tma_kernel, (unsigned)blocks, AM_THREADS, (size_t)2 * AM_THREADS * 12 * sizeof(double), st, a, n_tiles);
+        const uint64_t done = n_tiles * 2 * AM_THREADS;
+        if (done == n) return 0;
+        SoaArgs t = a;
+        for (int k = 0; k < 12; ++k) t.T[k] = a.T[k] + done;
+        if (a.E) t.E = a.E + done;
+        if (a.J3) t.J3 = a.J3 + done * 3;
+        if (a.H9) t.H9 = a.H9 + done * 9;
+        t.n = n - done;
+        TWG_LAUNCH(c, (amips_soa_kernel<2, true>), 1, AM_THREADS, (size_t)2 * AM_THREADS * 12 * sizeof(double), st, t);
+        return 0;
+    }
     const int tile = AM_THREADS * (vec ? 2 : 1);
     uint64_t blocks = (n + tile - 1) / tile;
     const uint64_t maxb = (uint64_t)c->sm_count * 16;

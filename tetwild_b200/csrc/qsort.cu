@@ -93,9 +93,14 @@ int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uin
                     const double** sorted_out) {
     TWG_CHECK(c, n < 0xffffffffull, TWG_ERR_INVALID_ARG, "at most 2^32-2 queries per call");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    // The keys are 30-bit Morton codes; only the top `bits` are sorted (stable): 24 bits = a 256^3 grid over the surface's
+    // box = three 8-bit radix passes instead of four. Order inside a cell does not matter to the traversals (a warp's group
+    // of 64 queries spans a cell or two either way).
+    static const int bits = [] { const char* e = getenv("TWG_SORT_BITS"); const int v = e ? atoi(e) : 24; return v < 8 ? 8 : (v > 30 ? 30 : v); }();
+    const int begin_bit = 30 - bits;
     size_t tmp_bytes = 0;
     TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                (int)n, 0, 30, st));
+                                                (int)n, begin_bit, 30, st));
     static const bool trace = getenv("TWG_TRACE") != nullptr;
     if (trace) fprintf(stderr, "[twg] sort lane=%d n=%llu tmp=%zu have=%zu\n", lane, (unsigned long long)n, tmp_bytes, c->dsort_bytes[lane]);
     const size_t kb = up(n * 4);
@@ -126,8 +131,8 @@ int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uin
         TWG_LAUNCH(c, qbounds_kernel, (unsigned)g, 256, 0, st, dP, n, bounds);
     }
     TWG_LAUNCH(c, qkeys_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, keys, vals);
-    TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 30, st));
-    c->launches += 5;  // cub: histogram + exclusive-sum + one onesweep pass per 8 key bits (library kernels)
+    TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, begin_bit, 30, st));
+    c->launches += 2 + (bits + 7) / 8;  // cub: histogram + exclusive-sum + one onesweep pass per 8 key bits (library kernels)
     *perm_out = vals2;
     if (sorted_out) {
         double* Pd = (double*)(base + 256 + 4 * kb + up(tmp_bytes));
