@@ -48,6 +48,35 @@ def test_point_triangle_distance_bit_exact(harness, oracle):
         assert d == d2 and np.array_equal(near, n2)
 
 
+def test_point_triangle_distance_every_outcome_class(harness, oracle):
+    """The product routine selects one of eight outcome classes by comparisons and then runs straight-line arithmetic
+    (tw_math.cuh::tri_sqdist_rec); queries ON vertices / edges / the facet, just off an edge line beyond its ends, and far
+    away reach every class and every region boundary. Bit-exact d2 and nearest point against the oracle."""
+    rng = np.random.default_rng(99)
+    for it in range(30000):
+        v = rng.normal(size=(3, 3)) * rng.choice([1, 0.01, 100])
+        k = it % 10
+        if k == 0:
+            p = v[rng.integers(3)].copy()
+        elif k == 1:
+            a, b = rng.choice(3, 2, replace=False)
+            p = v[a] + (v[b] - v[a]) * rng.uniform()
+        elif k == 2:
+            a, b = rng.choice(3, 2, replace=False)
+            p = v[a] + (v[b] - v[a]) * rng.uniform(-1, 2) + 1e-3 * rng.normal(size=3)
+        elif k == 3:
+            p = (v * rng.dirichlet([1, 1, 1])[:, None]).sum(0)
+        elif k == 4:
+            w = rng.uniform(-1, 2, 3)
+            p = (v * w[:, None]).sum(0) + rng.normal(size=3) * rng.choice([0, 1e-6, 1])
+        else:
+            p = rng.normal(size=3) * rng.choice([1, 0.02, 3, 300])
+        near = np.empty(3)
+        d = harness.hh_tri_sqdist(P(p), P(v[0]), P(v[1]), P(v[2]), P(near))
+        d2, n2 = oracle.point_triangle_sqdist(p, v[0], v[1], v[2])
+        assert d == d2 and np.array_equal(near, n2)
+
+
 def test_sampling_bit_exact(harness, oracle):
     rng = np.random.default_rng(4)
     for it in range(400):

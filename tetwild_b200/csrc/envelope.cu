@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* to
 //     on its own; the warp runs the routine when kLeafQuorum lanes are parked (or nothing else can advance), one facet
 //     per parked lane per round. Early exit is per query, as in the reference (mesh_AABB.cpp:489).
 constexpr int kFrontMaxDefault = 32;
-constexpr int kLeafQuorum = 16;
+constexpr int kLeafQuorumDefault = 16;
 template <int FM>
 struct FrontT {
     uint32_t node[FM];
@@ -67,7 +67,7 @@ struct FrontT {
 // MINB: resident CTAs per SM the register allocation is capped for (8 -> 64 registers, 32 warps per SM); FM: frontier cap
 template <int MINB, int FM>
 __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
-                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy) {
+                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy, int kLeafQuorum) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
@@ -609,13 +609,14 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     static const int group = [] { const char* e = getenv("TWG_ENV_GROUP"); int v = e ? atoi(e) : 64; return v < 32 ? 32 : (v > 4096 ? 4096 : v); }();
     static const int policy = [] { const char* e = getenv("TWG_ENV_POLICY"); return e ? atoi(e) : 1; }();
     static const int front = [] { const char* e = getenv("TWG_ENV_FRONT"); return e ? atoi(e) : kFrontMaxDefault; }();
+    static const int quorum = [] { const char* e = getenv("TWG_ENV_QUORUM"); const int v = e ? atoi(e) : kLeafQuorumDefault; return v < 1 ? 1 : (v > 32 ? 32 : v); }();
     const unsigned grid = grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8);
     if (front <= 16)
-        TWG_LAUNCH(c, (env_points_kernel<8, 16>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy);
+        TWG_LAUNCH(c, (env_points_kernel<8, 16>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy, quorum);
     else if (front >= 64)
-        TWG_LAUNCH(c, (env_points_kernel<8, 64>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy);
+        TWG_LAUNCH(c, (env_points_kernel<8, 64>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy, quorum);
     else
-        TWG_LAUNCH(c, (env_points_kernel<8, 32>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy);
+        TWG_LAUNCH(c, (env_points_kernel<8, 32>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy, quorum);
     if (trace) fprintf(stderr, "[twg] launched\n");
     return 0;
 }

@@ -58,9 +58,10 @@ struct WView {
 // third-order correction: with s = l2*y0 and e = 1 - s*y0 (exact to rounding through the fma), sqrt(l2) =
 // s*(1 + e/2 + 3e^2/8 + O(e^3)); the neglected term is < 2^-63 relative. 5 FP64 instructions after the seed, branch free
 // (CUDA's sqrt() adds a slow-path call per use; two Newton steps on the reciprocal root cost 8).
-// The +1e-300 only matters for a query ON a vertex (length 0): the factor then degenerates to a positive real.
+// The 1e-300 folded into the sum of squares only matters for a query ON a vertex (length 0): the factor then degenerates
+// to a positive real.
 __device__ __forceinline__ double norm3(double x, double y, double z) {
-    const double l2 = fma(x, x, fma(y, y, z * z)) + 1e-300;
+    const double l2 = fma(x, x, fma(y, y, fma(z, z, 1e-300)));
     double y0;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(l2));
     const double s = l2 * y0;
