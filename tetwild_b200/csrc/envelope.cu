@@ -516,27 +516,82 @@ __global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, c
             const int chunk = (total + 31) / 32;
             int sidx = lane * chunk;
             const int send = min(total, sidx + chunk);
-            if (sidx < send && !found_out) {
-                int lo = 0, hi = nrun - 1;  // last run with off <= sidx and cnt > 0 covering sidx
+            int r = 0, i = 0;
+            if (sidx < send) {
+                int lo = 0, hi = nrun - 1;  // last run with off <= sidx: the run that covers sample sidx
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
                     if (runs[mid].off <= sidx) lo = mid; else hi = mid - 1;
                 }
-                int r = lo;
+                r = lo;
                 while (runs[r].cnt == 0 || runs[r].off + runs[r].cnt <= sidx) ++r;  // skip empty runs that share the offset
-                int i = sidx - runs[r].off;
-                for (; sidx < send; ++sidx) {
+                i = sidx - runs[r].off;
+            }
+            auto next_sample = [&]() -> tw::V3 {  // sample sidx of the concatenated runs; advances the cursor
+                while (i >= runs[r].cnt) { ++r; i = 0; }
+                tw::V3 p;
+                if (r >= fixed) p = tw::row_sample(tw::mk(runs[r].ox, runs[r].oy, runs[r].oz), P.n01, sd, i);
+                else if (r == 0) p = tw::edge_sample(P.v0, P.n01, sd, i);
+                else if (r == 1) p = (P.kind == 0) ? (i == 0 ? P.v0 : (i == 1 ? P.v1 : P.v2)) : (i == 0 ? P.v1 : P.v2);
+                else if (r == 2) p = tw::edge_sample(P.v1, P.n12, sd, i + 1);
+                else p = tw::edge_sample(P.v2, P.n20, sd, i + 1);
+                ++i; ++sidx;
+                return p;
+            };
+            if (!leaves) {
+                // face too large for a candidate list: every lane descends from the root per sample (hint first)
+                while (sidx < send && !found_out) {
                     if (flag[wib]) break;
-                    while (i >= runs[r].cnt) { ++r; i = 0; }
-                    tw::V3 p;
-                    if (r >= fixed) p = tw::row_sample(tw::mk(runs[r].ox, runs[r].oy, runs[r].oz), P.n01, sd, i);
-                    else if (r == 0) p = tw::edge_sample(P.v0, P.n01, sd, i);
-                    else if (r == 1) p = (P.kind == 0) ? (i == 0 ? P.v0 : (i == 1 ? P.v1 : P.v2)) : (i == 0 ? P.v1 : P.v2);
-                    else if (r == 2) p = tw::edge_sample(P.v1, P.n12, sd, i + 1);
-                    else p = tw::edge_sample(P.v2, P.n20, sd, i + 1);
-                    const bool is_out = leaves ? sample_out_cands(S, p, eps2, thr, prev, cand, ncand) : sample_out(S, p, eps2, prev, top, topN);
-                    if (is_out) { found_out = true; flag[wib] = 1; break; }
-                    ++i;
+                    const tw::V3 p = next_sample();
+                    if (sample_out(S, p, eps2, prev, top, topN)) { found_out = true; flag[wib] = 1; }
+                }
+            } else {
+                // ---- warp-synchronous rounds over three stages:
+                //   FETCH  generate the lane's next sample; it goes to LEAF on the hint facet (the facet that held the lane's
+                //          previous sample, LocalOperations.cpp:1080-1082) or, without a hint, to SCAN
+                //   LEAF   exact point-triangle test of one facet; within eps -> the sample is IN (next FETCH), else SCAN
+                //   SCAN   FP32 box bounds of the face's candidate leaves from where the lane stopped; first box within eps ->
+                //          LEAF on that facet; list exhausted -> the sample, hence the face, is OUT
+                // A face inside the envelope keeps all lanes in FETCH -> LEAF(hint) lockstep; per-lane loops left 8 of 32
+                // lanes active per instruction (ncu) because hint hits, scans and leaf tests interleaved at random.
+                enum { FETCH = 0, LEAF = 1, SCAN = 2, DONE = 3 };
+                int stage = (sidx < send && !found_out) ? FETCH : DONE;
+                tw::V3 p = tw::mk(0, 0, 0);
+                twd::PointF q = twd::bracket(p);
+                uint32_t leaf_pos = 0;
+                int scan_i = 0;
+                for (;;) {
+                    if (__ballot_sync(full, stage != DONE) == 0u || flag[wib]) break;
+                    // fixed order SCAN -> FETCH -> LEAF: scanning lanes find their next candidate and fetching lanes their next
+                    // sample first (cheap stages, subsets of the warp), so that the expensive exact test then runs ONCE for
+                    // every lane that has a facet to test -- hint facets and scan candidates in the same round
+                    if (stage == SCAN) {
+                        bool hit = false;
+                        for (; scan_i < ncand; ++scan_i) {
+                            const float d = twd::box_d2_lb(q, cand->box[scan_i][0], cand->box[scan_i][1], cand->box[scan_i][2], cand->box[scan_i][3],
+                                                           cand->box[scan_i][4], cand->box[scan_i][5]);
+                            const uint32_t pos = cand->node[scan_i] - S.nLeafP;
+                            if (d <= thr && pos != prev && pos < S.nF) { leaf_pos = pos; hit = true; ++scan_i; break; }
+                        }
+                        if (hit) stage = LEAF;
+                        else { found_out = true; flag[wib] = 1; stage = DONE; }
+                    }
+                    __syncwarp();
+                    if (flag[wib]) break;
+                    if (stage == FETCH) {
+                        p = next_sample();
+                        q = twd::bracket(p);
+                        scan_i = 0;
+                        if (prev != TWG_NO_FACET) { leaf_pos = prev; stage = LEAF; }
+                        else stage = SCAN;
+                    }
+                    __syncwarp();
+                    if (stage == LEAF) {
+                        double s_, t_; tw::V3 nd; bool deg;
+                        if (twd::facet_d2(S, leaf_pos, p, s_, t_, nd, deg) <= eps2) { prev = leaf_pos; stage = (sidx < send) ? FETCH : DONE; }
+                        else stage = SCAN;
+                    }
+                    __syncwarp();
                 }
             }
             __syncwarp();
