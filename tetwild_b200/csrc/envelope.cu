@@ -410,7 +410,7 @@ struct __align__(16) FaceRun {
     int off;            // samples before this run (exclusive scan)
 };
 
-__global__ void __launch_bounds__(kEnvThreads) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
+__global__ void __launch_bounds__(kEnvThreads, 4) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
                                                                uint32_t flags, uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
