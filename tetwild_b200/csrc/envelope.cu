@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceVi
 }
 
 constexpr int kNearRun = 8;  // consecutive sorted queries per lane and claim
-__global__ void __launch_bounds__(kEnvThreads) nearest_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm, uint64_t n,
+__global__ void __launch_bounds__(kEnvThreads, 8) nearest_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm, uint64_t n,
                                                              uint32_t* __restrict__ facet, double* __restrict__ nearest, double* __restrict__ d2out,
                                                              unsigned long long* counter) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -686,7 +686,7 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm, s->sort_box));
     const int lane = twg_lane_of(c, st);
     TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
-    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, (n + 32 * kNearRun - 1) / (32 * kNearRun), kEnvThreads / 32, 5), kEnvThreads, top_smem(s), st, view_of(s), dP,
+    TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, (n + 32 * kNearRun - 1) / (32 * kNearRun), kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), dP,
                perm, n, dFacet, dNearest, dD2, s->counters + lane);
     return 0;
 }
