@@ -717,6 +717,18 @@ static int points_host(twg_surface* s, int what, const double* P, uint64_t n, do
     const uint64_t cmax = n < chunk ? n : chunk;
     const size_t pb = up(cmax * 24), ob = up(cmax), fb = up(cmax * 4), nb = up(cmax * 24), db = up(cmax * 8);
     for (int k = 0; k < TWG_NUM_STREAMS; ++k) TWG_TRY(twg_ensure_scratch(c, k, pb + ob + fb + nb + db));
+    if (what == 0 && n <= 16384) {  // a few points (EdgeCollapser.cpp:322 asks for one): pinned slabs, one copy each way
+        TWG_TRY(twg_ensure_pinned(c, up(n * 24), up(n)));
+        cudaStream_t st = c->streams[0];
+        char* base = (char*)c->dscratch[0];
+        memcpy(c->pin_in[0], P, n * 24);
+        TWG_CUDA(c, cudaMemcpyAsync(base, c->pin_in[0], n * 24, cudaMemcpyHostToDevice, st));
+        TWG_TRY(twg_envelope_points_out_dev(s, (const double*)base, n, eps2, (uint8_t*)(base + pb), st));
+        TWG_CUDA(c, cudaMemcpyAsync(c->pin_out[0], base + pb, n, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+        memcpy(out, c->pin_out[0], n);
+        return 0;
+    }
     int slot = 0;
     for (uint64_t b = 0; b < n; b += chunk, slot = (slot + 1) % TWG_NUM_STREAMS) {
         const uint64_t m = (n - b < chunk) ? (n - b) : chunk;
@@ -768,10 +780,16 @@ int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, do
     TWG_TRY(twg_ensure_scratch(c, 0, up(n * 72) + up(n)));
     char* base = (char*)c->dscratch[0];
     cudaStream_t st = c->streams[0];
-    TWG_CUDA(c, cudaMemcpyAsync(base, tris, n * 72, cudaMemcpyHostToDevice, st));
+    const bool small = n <= 4096;  // the faces of one local operation: stage through pinned slabs (pageable copies cost ~10 us each)
+    if (small) {
+        TWG_TRY(twg_ensure_pinned(c, up(n * 72), up(n)));
+        memcpy(c->pin_in[0], tris, n * 72);
+    }
+    TWG_CUDA(c, cudaMemcpyAsync(base, small ? (const void*)c->pin_in[0] : (const void*)tris, n * 72, cudaMemcpyHostToDevice, st));
     TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)base, n, sd, eps2, flags, (uint8_t*)(base + up(n * 72)), st));
-    TWG_CUDA(c, cudaMemcpyAsync(out, base + up(n * 72), n, cudaMemcpyDeviceToHost, st));
+    TWG_CUDA(c, cudaMemcpyAsync(small ? (void*)c->pin_out[0] : (void*)out, base + up(n * 72), n, cudaMemcpyDeviceToHost, st));
     TWG_CUDA(c, cudaStreamSynchronize(st));
+    if (small) memcpy(out, c->pin_out[0], n);
     return 0;
 }
 

@@ -182,6 +182,7 @@ unsigned grid_for(twg_ctx* c, uint64_t items, int per_block, int waves) {
     return (unsigned)b;
 }
 size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+constexpr uint64_t kSmallCall = 8192;  // calls up to this many units take the packed, pinned, one-copy-each-way path
 
 int grow(twg_mesh* m, uint32_t nV, uint64_t nT) {
     twg_ctx* c = m->ctx;
@@ -384,6 +385,27 @@ int twg_mesh_vertex_ring_ejh(twg_mesh* m, const int32_t* v_ids, uint64_t n, doub
     TWG_TRY(twg_mesh_build_rings(m));
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->streams[0];
+    if (n <= kSmallCall) {
+        // a handful of rings (what one un-batched Newton step of the scheduler asks for): latency is everything. Ids go
+        // through a pinned slab in ONE copy, the four result arrays come back packed in ONE copy (each extra cudaMemcpy of a
+        // pageable buffer costs ~10 us: 53 -> ~25 us per call).
+        const size_t ib = up256(n * 4), eb = up256(n * 8), jb = up256(n * 24), hb = up256(n * 72), kb = up256(n);
+        TWG_TRY(twg_ensure_pinned(c, ib, eb + jb + hb + kb));
+        TWG_TRY(twg_ensure_scratch(c, 0, ib + eb + jb + hb + kb));
+        char* d = (char*)c->dscratch[0];
+        char* ho = (char*)c->pin_out[0];
+        memcpy(c->pin_in[0], v_ids, n * 4);
+        TWG_CUDA(c, cudaMemcpyAsync(d, c->pin_in[0], n * 4, cudaMemcpyHostToDevice, st));
+        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, (const int32_t*)m->T, m->adj_tets, m->adj_off, (const int32_t*)d, n, (double*)(d + ib),
+                                              (double*)(d + ib + eb), (double*)(d + ib + eb + jb), (uint8_t*)(d + ib + eb + jb + hb), st));
+        TWG_CUDA(c, cudaMemcpyAsync(ho, d + ib, eb + jb + hb + (ok ? n : 0), cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+        memcpy(E, ho, n * 8);
+        memcpy(J3, ho + eb, n * 24);
+        memcpy(H9, ho + eb + jb, n * 72);
+        if (ok) memcpy(ok, ho + eb + jb + hb, n);
+        return 0;
+    }
     // chunks on two streams so that the result copies of one chunk overlap the kernel of the next
     const uint64_t chunk = 1ull << 20;
     const uint64_t cm = n < chunk ? n : chunk;
@@ -431,6 +453,18 @@ int twg_mesh_ring_ejh(twg_mesh* m, const int32_t* t_ids, const uint64_t* group_o
     TWG_TRY(stage(c, o, (const double*)nullptr, 9 * nG, &dH));
     TWG_TRY(stage(c, o, (const uint8_t*)nullptr, nG, &dK));
     TWG_TRY(twg_amips_ring_ejh_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, dI, dO, dC, nG, dE, dJ, dH, dK, st));
+    if (nG <= kSmallCall) {  // E | J | H | ok are consecutive in the scratch slab: one packed copy through pinned memory
+        const size_t eb = up256(nG * 8), jb = up256(nG * 24), hb = up256(nG * 72);
+        TWG_TRY(twg_ensure_pinned(c, 256, eb + jb + hb + up256(nG)));
+        char* ho = (char*)c->pin_out[0];
+        TWG_CUDA(c, cudaMemcpyAsync(ho, dE, eb + jb + hb + (ok ? nG : 0), cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+        memcpy(E, ho, nG * 8);
+        memcpy(J3, ho + eb, nG * 24);
+        memcpy(H9, ho + eb + jb, nG * 72);
+        if (ok) memcpy(ok, ho + eb + jb + hb, nG);
+        return 0;
+    }
     TWG_CUDA(c, cudaMemcpyAsync(E, dE, nG * 8, cudaMemcpyDeviceToHost, st));
     TWG_CUDA(c, cudaMemcpyAsync(J3, dJ, nG * 24, cudaMemcpyDeviceToHost, st));
     TWG_CUDA(c, cudaMemcpyAsync(H9, dH, nG * 72, cudaMemcpyDeviceToHost, st));
