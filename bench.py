@@ -345,6 +345,16 @@ def run_gpu(args, parts):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    unpinned = []
+
+    def pin(t):
+        """page-lock a host tensor; a box that cannot lock that much memory (8 ranks x ~10 GB) still runs, with pageable buffers"""
+        try:
+            return t.pin_memory()
+        except RuntimeError:
+            unpinned.append(int(t.numel() * t.element_size()))
+            return t
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -461,13 +471,13 @@ def run_gpu(args, parts):
             sd, eps, eps2 = synth.state_eps(1e-3)
             S = tw.Surface(ctx, V, F)
             P = envelope_points_fast(V, F, n, eps, seed=20240501 + rank)
-            hP = torch.from_numpy(P).pin_memory()
+            hP = pin(torch.from_numpy(P))
             dP = hP.to(dev, non_blocking=True)
             pipe = Pipe(n)
             step = lambda: S.points_out_dev(dP.data_ptr(), n, eps2, pipe.out().data_ptr(), sh)  # noqa: E731
             ms, kms, launches, win = timed(step, pipe.gather, pipe.drain)
             dO = pipe.last()
-            hO = torch.empty(n, dtype=torch.uint8).pin_memory()
+            hO = pin(torch.empty(n, dtype=torch.uint8))
             e2e_s = e2e_timed(lambda: S.points_out(hP.numpy(), eps2, out=hO.numpy()))
             out_frac = float(dO.float().mean().item())
             # parity inside the bench: a 100k sample of this very batch against the oracle (decisions must be identical)
@@ -485,14 +495,14 @@ def run_gpu(args, parts):
             sd, eps, eps2 = synth.state_eps(1e-3)
             S = tw.Surface(ctx, V, F)
             P = envelope_points_fast(V, F, n, eps, seed=20240501 + rank)
-            hP = torch.from_numpy(P).pin_memory()
+            hP = pin(torch.from_numpy(P))
             dP = hP.to(dev, non_blocking=True)
             dF = torch.empty(n, device=dev, dtype=torch.int32)
             dN = torch.empty((n, 3), device=dev, dtype=torch.float64)
             dD = torch.empty(n, device=dev, dtype=torch.float64)
             step = lambda: S.nearest_dev(dP.data_ptr(), n, dF.data_ptr(), dN.data_ptr(), dD.data_ptr(), sh)  # noqa: E731
             ms, kms, launches, win = timed(step)
-            hF, hN, hD = torch.empty(n, dtype=torch.int32).pin_memory(), torch.empty((n, 3), dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory()
+            hF, hN, hD = pin(torch.empty(n, dtype=torch.int32)), pin(torch.empty((n, 3), dtype=torch.float64)), pin(torch.empty(n, dtype=torch.float64))
             outs = (hF.numpy().view(np.uint32), hN.numpy(), hD.numpy())
             e2e_s = e2e_timed(lambda: S.nearest(hP.numpy(), out=outs))
             mism = None
@@ -509,7 +519,7 @@ def run_gpu(args, parts):
             sd, eps, eps2 = synth.state_eps(1e-3)
             S = tw.Surface(ctx, V, F)
             T = synth.face_queries(V, F, n, FACE_EDGE, eps, seed=3 + rank)
-            hT = torch.from_numpy(T).pin_memory()
+            hT = pin(torch.from_numpy(T))
             dTr = hT.to(dev, non_blocking=True)
             pipe = Pipe(n)
             step = lambda: S.faces_out_dev(dTr.data_ptr(), n, sd, eps2, pipe.out().data_ptr(), sh)  # noqa: E731
@@ -535,9 +545,9 @@ def run_gpu(args, parts):
             ptrs = [dT[k].data_ptr() for k in range(12)]
             step = lambda: ctx.amips_ejh_soa_dev(ptrs, dE.data_ptr(), dJ.data_ptr(), dH.data_ptr(), n, sh)  # noqa: E731
             ms, kms, launches, win = timed(step)
-            hT = torch.empty((12, n), dtype=torch.float64).pin_memory()
+            hT = pin(torch.empty((12, n), dtype=torch.float64))
             hT.copy_(dT)
-            hE, hJ, hH = (torch.empty(s, dtype=torch.float64).pin_memory() for s in ((n,), (n, 3), (n, 9)))
+            hE, hJ, hH = (pin(torch.empty(s, dtype=torch.float64)) for s in ((n,), (n, 3), (n, 9)))
             e2e_s = e2e_timed(lambda: ctx.amips_ejh_soa(hT.numpy(), out=(hE.numpy(), hJ.numpy(), hH.numpy())))
             mism = None
             if rank == 0:
@@ -557,7 +567,7 @@ def run_gpu(args, parts):
             del dT, dE, dJ, dH, hT, hE, hJ, hH
         elif part == "amips_quality":
             dV, dT4, dOff, dCen = rings_on_device(n, 7 + rank, dev)
-            hV, hT4 = dV.cpu().pin_memory(), dT4.cpu().pin_memory()
+            hV, hT4 = pin(dV.cpu()), pin(dT4.cpu())
             nV = int(dV.shape[0])
             del dV, dT4, dOff, dCen
             torch.cuda.empty_cache()
@@ -565,7 +575,7 @@ def run_gpu(args, parts):
             dQ = torch.empty(n, device=dev, dtype=torch.float64)
             step = lambda: M.quality_dev(0, n, dQ.data_ptr(), sh)  # noqa: E731
             ms, kms, launches, win = timed(step)
-            hQ = torch.empty(n, dtype=torch.float64).pin_memory()
+            hQ = pin(torch.empty(n, dtype=torch.float64))
             e2e_s = e2e_timed(lambda: M.quality(out=hQ.numpy()))
             mism = None
             if rank == 0:
@@ -592,7 +602,7 @@ def run_gpu(args, parts):
             step = lambda: ctx.amips_ring_ejh_dev(dV.data_ptr(), nV, dT4.data_ptr(), n, 0, dOff.data_ptr(), dCen.data_ptr(), nG, dE.data_ptr(),  # noqa: E731
                                                   dJ.data_ptr(), dH.data_ptr(), dOk.data_ptr(), sh)
             ms, kms, launches, win = timed(step)
-            hV, hT4, hOff, hCen = dV.cpu().pin_memory(), dT4.cpu().pin_memory(), dOff.cpu().pin_memory(), dCen.cpu().pin_memory()
+            hV, hT4, hOff, hCen = pin(dV.cpu()), pin(dT4.cpu()), pin(dOff.cpu()), pin(dCen.cpu())
             ship_s = e2e_timed(lambda: ctx.amips_ring_ejh(hV.numpy(), hT4.numpy(), hOff.numpy().view(np.uint64), hCen.numpy()))
             # the integration the scheduler uses: the tet mesh is RESIDENT on the device (uploaded once,
             # kept in step by scatter updates), a Newton batch ships 4 B of vertex id per ring in and 105 B per ring out
@@ -600,8 +610,8 @@ def run_gpu(args, parts):
             M = tw.TetMesh(ctx, hV.numpy(), hT4.numpy())
             M.build_rings()
             mesh_build_s = time.perf_counter() - t0
-            hE, hJ, hH = (torch.empty(sz, dtype=torch.float64).pin_memory() for sz in ((nG,), (nG, 3), (nG, 9)))
-            hOk = torch.empty(nG, dtype=torch.uint8).pin_memory()
+            hE, hJ, hH = (pin(torch.empty(sz, dtype=torch.float64)) for sz in ((nG,), (nG, 3), (nG, 9)))
+            hOk = pin(torch.empty(nG, dtype=torch.uint8))
             outs = (hE.numpy(), hJ.numpy(), hH.numpy(), hOk.numpy())
             e2e_s = e2e_timed(lambda: M.vertex_ring_ejh(hCen.numpy(), out=outs))
             same = bool(np.array_equal(hE.numpy(), dE.cpu().numpy()) and np.array_equal(hH.numpy(), dH.cpu().numpy()))
@@ -641,9 +651,9 @@ def run_gpu(args, parts):
             step = lambda: Wt.eval_dev(dQ.data_ptr(), n, 0, pipe.out().data_ptr(), sh)  # noqa: E731
             ms, kms, launches, win = timed(step, pipe.gather, pipe.drain)
             dK = pipe.last()
-            hQ = torch.empty((n, 3), dtype=torch.float64).pin_memory()
+            hQ = pin(torch.empty((n, 3), dtype=torch.float64))
             hQ.copy_(dQ)
-            hK = torch.empty(n, dtype=torch.uint8).pin_memory()
+            hK = pin(torch.empty(n, dtype=torch.uint8))
             e2e_s = e2e_timed(lambda: Wt.eval(hQ.numpy(), want_w=False, out=(None, hK.numpy())))
             mism = None
             if rank == 0:
@@ -686,7 +696,7 @@ def run_gpu(args, parts):
                "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                "data": "synthetic", "config": dict(h["config"], parallelism="replicated surface, batches split by rank, NCCL all_gather of decisions overlapped with the next step's kernels (double-buffered)" if world > 1 else "single GPU"),
                "roofline": h["roofline"], "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "clocks": h["clocks"],
-               "cpu_baseline": h.get("cpu_baseline"), "extra": h.get("extra"),
+               "cpu_baseline": h.get("cpu_baseline"), "extra": dict(h.get("extra") or {}, host_buffers_not_page_locked_bytes=sum(unpinned)),
                "parts": {p: results[p] for p in parts if p != head}}
         print(json.dumps(out))
     if world > 1:
