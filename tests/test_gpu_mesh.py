@@ -170,6 +170,20 @@ def test_invalid_ids_fail_loudly(ctx, grid):
         M.vertex_ring_ejh(np.array([-1], dtype=np.int32))
 
 
+def test_out_of_range_indices_are_refused(ctx, grid):
+    """host entry points validate indices before anything reaches the device"""
+    V, T = grid
+    bad = T.copy(); bad[7, 2] = len(V)
+    with pytest.raises(tw.TetWildGPUError):
+        tw.TetMesh(ctx, V, bad)
+    Vs, Fs = synth.uv_sphere(12, 12)
+    Fb = Fs.copy(); Fb[3, 1] = len(Vs)
+    with pytest.raises(tw.TetWildGPUError):
+        tw.Surface(ctx, Vs, Fb)
+    with pytest.raises(tw.TetWildGPUError):
+        tw.Winding(ctx, Vs, Fb)
+
+
 def test_empty_mesh(ctx):
     M = tw.TetMesh(ctx, np.zeros((0, 3)), np.zeros((0, 4), dtype=np.int32))
     assert M.num_tets == 0 and len(M.quality()) == 0

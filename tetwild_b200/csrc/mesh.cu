@@ -233,6 +233,10 @@ extern "C" {
 int twg_mesh_create(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets4, uint64_t nT, twg_mesh** out) {
     TWG_CHECK(c, c && out && (V || nV == 0) && (tets4 || nT == 0), TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, nT < (1ull << 29), TWG_ERR_INVALID_ARG, "at most 2^29 tets");
+    for (uint64_t t = 0; t < nT; ++t)
+        if (tets4[4 * t] >= 0)  // a negative first index marks a removed slot
+            for (int k = 0; k < 4; ++k)
+                TWG_CHECK(c, tets4[4 * t + k] >= 0 && (uint32_t)tets4[4 * t + k] < nV, TWG_ERR_INVALID_ARG, "tet references a vertex out of range");
     *out = nullptr;
     TWG_CUDA(c, cudaSetDevice(c->device));
     twg_mesh* m = new twg_mesh;

@@ -222,6 +222,7 @@ int twg_surface_create_dev(twg_ctx* c, const double* dV, uint32_t nV, const uint
 int twg_surface_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_surface** out) {
     TWG_CHECK(c, c && V && F && out, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, nF > 0 && nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "surface must have 1 .. 2^31-2 facets");
+    for (size_t k = 0; k < 3 * (size_t)nF; ++k) TWG_CHECK(c, F[k] < nV, TWG_ERR_INVALID_ARG, "facet references a vertex out of range");
     TWG_CUDA(c, cudaSetDevice(c->device));
     double* dV = nullptr;
     uint32_t* dF = nullptr;

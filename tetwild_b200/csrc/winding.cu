@@ -550,6 +550,7 @@ void twg_winding_destroy(twg_winding* w) {
 
 int twg_winding_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out) {
     TWG_CHECK(c, c && out && (nF == 0 || (V && F)), TWG_ERR_INVALID_ARG, "null argument");
+    for (size_t k = 0; k < 3 * (size_t)nF; ++k) TWG_CHECK(c, F[k] < nV, TWG_ERR_INVALID_ARG, "facet references a vertex out of range");
     TWG_CUDA(c, cudaSetDevice(c->device));
     twg_winding* w = new twg_winding;
     w->ctx = c;
