@@ -26,6 +26,7 @@
 // FP64-pipe-bound by design (no tensor-core formulation exists for sqrt / cross-product chains).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include "common.cuh"
 
@@ -284,7 +285,57 @@ struct HostTree {
     uint32_t nBlkP = 1;
 };
 
+// ---- small host-side parallel helpers for the hierarchy build (std::thread, no OpenMP dependency)
+unsigned host_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 1;
+    return n > 16 ? 16 : n;
+}
+// fn(begin, end, part) over [0, n) cut into `parts` contiguous ranges, one thread each
+template <class FN>
+void parallel_ranges(size_t n, unsigned parts, FN fn, size_t min_items = 4096) {
+    if (parts <= 1 || n < min_items) { fn((size_t)0, n, 0u); return; }
+    std::vector<std::thread> pool;
+    for (unsigned p = 0; p < parts; ++p) pool.emplace_back([&, p] { fn(n * p / parts, n * (p + 1) / parts, p); });
+    for (auto& t : pool) t.join();
+}
+// sort = per-thread std::sort of equal chunks + rounds of pairwise in-place merges (deterministic for a strict weak order;
+// elements that compare equal may land in any relative order, like std::sort)
+template <class IT, class CMP>
+void parallel_sort(IT first, IT last, CMP cmp) {
+    const size_t n = (size_t)(last - first);
+    unsigned parts = host_threads();
+    while (parts > 1 && n / parts < 65536) parts >>= 1;
+    unsigned p2 = 1;
+    while (p2 * 2 <= parts) p2 *= 2;  // power of two chunks
+    if (p2 <= 1) { std::sort(first, last, cmp); return; }
+    auto bound = [&](unsigned k) { return first + (ptrdiff_t)(n * k / p2); };
+    parallel_ranges(p2, p2, [&](size_t b, size_t e, unsigned) { for (size_t k = b; k < e; ++k) std::sort(bound((unsigned)k), bound((unsigned)k + 1), cmp); }, 0);
+    for (unsigned width = 1; width < p2; width *= 2) {
+        const unsigned pairs = p2 / (2 * width);
+        parallel_ranges(pairs, pairs, [&](size_t b, size_t e, unsigned) {
+            for (size_t k = b; k < e; ++k) {
+                const unsigned lo = (unsigned)k * 2 * width;
+                std::inplace_merge(bound(lo), bound(lo + width), bound(lo + 2 * width), cmp);
+            }
+        }, 0);
+    }
+}
+
+struct PhaseTimer {  // TWG_TRACE=1: wall time of the build phases on stderr
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTimer() : on(getenv("TWG_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[twg] winding build: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, uint32_t kLeaf, HostTree& T) {
+    PhaseTimer tm;
     // 1. merge exactly coincident vertices (libigl: remove_duplicate_vertices(V,F,0.0,...))
     std::vector<uint32_t> idx(nV), canon(nV);
     for (uint32_t i = 0; i < nV; ++i) idx[i] = i;
@@ -295,7 +346,7 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
         if (p[2] != q[2]) return p[2] < q[2];
         return a < b;
     };
-    std::sort(idx.begin(), idx.end(), vless);
+    parallel_sort(idx.begin(), idx.end(), vless);
     for (uint32_t i = 0; i < nV; ++i) {
         if (i > 0) {
             const double *p = V + 3 * (size_t)idx[i], *q = V + 3 * (size_t)idx[i - 1];
@@ -303,6 +354,7 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
         }
         canon[idx[i]] = idx[i];
     }
+    tm.lap("1 vertex merge");
     // 2. kd order of the facets: the heap node that owns blocks [i*2^h, (i+1)*2^h) must be a COMPACT patch, because the
     //    price of a far sub-mesh is the length of its boundary. Recursive split of the centroid set at the block-aligned
     //    midpoint along the longest axis of its bounding box (libigl's WindingNumberAABB splits the same way); a plain
@@ -375,6 +427,7 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
     std::vector<uint32_t> SF(3 * (size_t)nF);
     for (uint32_t j = 0; j < nF; ++j)
         for (int k = 0; k < 3; ++k) SF[3 * (size_t)j + k] = canon[F[3 * (size_t)order[j] + k]];
+    tm.lap("2 kd order");
     // 3. heap over leaf blocks
     int depth = 0;
     while ((1u << depth) < nBlkP) ++depth;
@@ -383,18 +436,21 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
     std::vector<double> blo(3 * (size_t)nNodes, DBL_MAX), bhi(3 * (size_t)nNodes, -DBL_MAX);
     std::vector<uint32_t> nfac(nNodes, 0), foff(nNodes, 0);
     T.tris.assign(9 * ((size_t)nF + 2), 0.0);  // +2: bulk copies round the triangle count up to even
-    for (uint32_t j = 0; j < nF; ++j) {
-        const uint32_t node = nBlkP + j / kLeaf;
-        for (int k = 0; k < 3; ++k) {
-            const double* p = V + 3 * (size_t)SF[3 * (size_t)j + k];
-            for (int c = 0; c < 3; ++c) {
-                T.tris[9 * (size_t)j + 3 * k + c] = p[c];
-                blo[3 * (size_t)node + c] = std::min(blo[3 * (size_t)node + c], p[c]);
-                bhi[3 * (size_t)node + c] = std::max(bhi[3 * (size_t)node + c], p[c]);
+    parallel_ranges(nBlkP, host_threads(), [&](size_t b0, size_t b1, unsigned) {  // a leaf block is owned by one thread
+        const uint64_t j0 = std::min<uint64_t>((uint64_t)b0 * kLeaf, nF), j1 = std::min<uint64_t>((uint64_t)b1 * kLeaf, nF);
+        for (uint64_t j = j0; j < j1; ++j) {
+            const uint32_t node = nBlkP + (uint32_t)(j / kLeaf);
+            for (int k = 0; k < 3; ++k) {
+                const double* p = V + 3 * (size_t)SF[3 * (size_t)j + k];
+                for (int c = 0; c < 3; ++c) {
+                    T.tris[9 * (size_t)j + 3 * k + c] = p[c];
+                    blo[3 * (size_t)node + c] = std::min(blo[3 * (size_t)node + c], p[c]);
+                    bhi[3 * (size_t)node + c] = std::max(bhi[3 * (size_t)node + c], p[c]);
+                }
             }
+            nfac[node]++;
         }
-        nfac[node]++;
-    }
+    });
     for (uint32_t b = 0; b < nBlkP; ++b) foff[nBlkP + b] = std::min((uint64_t)b * kLeaf, (uint64_t)nF);
     for (uint32_t i = nBlkP - 1; i >= 1; --i) {
         for (int c = 0; c < 3; ++c) {
@@ -404,6 +460,7 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
         nfac[i] = nfac[2 * i] + nfac[2 * i + 1];
         foff[i] = foff[2 * i];
     }
+    tm.lap("3 heap boxes");
     // 4. exterior edges of every node
     std::vector<HalfEdge> he;
     he.reserve(3 * (size_t)nF);
@@ -417,7 +474,9 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
             else { h.key = ((uint64_t)b << 32) | a; h.dir = -1; }
             he.push_back(h);
         }
-    std::sort(he.begin(), he.end(), [](const HalfEdge& x, const HalfEdge& y) { return x.key < y.key; });
+    tm.lap("4a half-edge list");
+    parallel_sort(he.begin(), he.end(), [](const HalfEdge& x, const HalfEdge& y) { return x.key < y.key; });
+    tm.lap("4b half-edge sort");
     std::vector<CapRec> recs;
     recs.reserve(2 * (size_t)nF);
     std::vector<std::pair<uint32_t, int32_t>> per;  // (node, net) scratch
@@ -445,6 +504,7 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
         }
         s = e;
     }
+    tm.lap("4c exterior edges");
     // 5. bucket by node, trace each node's exterior edges into polylines, choose the apex, cut the polylines at it
     std::vector<uint32_t> cnt(nNodes + 1, 0);
     for (auto& r : recs) cnt[r.node + 1]++;
@@ -455,12 +515,29 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
         for (auto& r : recs) sorted[cur[r.node]++] = r;
     }
     T.nodes.assign(nNodes, WNode{});
-    T.caps.clear();
-    T.caps.reserve(4 * (recs.size() + recs.size() / 4) + 16);
+    // nodes are independent: every thread traces a contiguous range of nodes into its own cap array (offsets local to the
+    // part), the parts are then concatenated in node order, which reproduces the serial layout exactly
+    const unsigned parts5 = (nNodes >= 4096) ? host_threads() : 1u;
+    std::vector<std::vector<double>> part_caps(parts5);
+    // ranges of nodes with equal numbers of edge records (the few nodes near the root carry the longest caps)
+    std::vector<uint32_t> part_first(parts5 + 1, nNodes);
+    part_first[0] = 0;
+    for (unsigned p = 1; p < parts5; ++p) {
+        const uint64_t target = (uint64_t)recs.size() * p / parts5;
+        part_first[p] = (uint32_t)(std::upper_bound(cnt.begin(), cnt.begin() + nNodes, (uint32_t)target) - cnt.begin());
+        if (part_first[p] < part_first[p - 1]) part_first[p] = part_first[p - 1];
+        if (part_first[p] > nNodes) part_first[p] = nNodes;
+    }
+    {
+    std::vector<std::thread> pool5;
+    auto trace_part = [&](unsigned part) {
+    const size_t n0 = part_first[part], n1 = part_first[part + 1];
+    std::vector<double>& caps = part_caps[part];
+    if (n1 > n0) caps.reserve(4 * ((size_t)(cnt[n1] - cnt[n0]) + (cnt[n1] - cnt[n0]) / 4) + 16);
     std::vector<uint32_t> chain;        // vertex ids of all polylines of one node, back to back
     std::vector<uint32_t> chain_start;  // offsets into `chain`
     std::vector<uint8_t> used;
-    for (uint32_t i = 1; i < nNodes; ++i) {
+    for (uint32_t i = (uint32_t)std::max<size_t>(n0, 1); i < (uint32_t)n1; ++i) {
         WNode& nd = T.nodes[i];
         for (int c = 0; c < 3; ++c) {
             nd.lo[c] = nfac[i] ? nextafterf((float)blo[3 * (size_t)i + c], -INFINITY) : INFINITY;
@@ -468,7 +545,7 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
         }
         nd.tri_off = foff[i];
         nd.tri_cnt = nfac[i];
-        nd.cap_off = (uint32_t)(T.caps.size() / 4);
+        nd.cap_off = (uint32_t)(caps.size() / 4);  // local to the part; rebased below
         nd.cap_cnt = 0;
         nd.apex[0] = nd.apex[1] = nd.apex[2] = 0.0;
         const uint32_t e0 = cnt[i], e1 = cnt[i + 1];
@@ -508,8 +585,8 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
                 if (!end) { ++run; continue; }
                 if (run >= 2) {
                     for (uint32_t q = k - run; q < k; ++q) {
-                        for (int c = 0; c < 3; ++c) T.caps.push_back(V[3 * (size_t)chain[q] + c]);
-                        T.caps.push_back(q == k - run ? 1.0 : 0.0);
+                        for (int c = 0; c < 3; ++c) caps.push_back(V[3 * (size_t)chain[q] + c]);
+                        caps.push_back(q == k - run ? 1.0 : 0.0);
                         nd.cap_cnt++;
                     }
                 }
@@ -517,7 +594,27 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
             }
         }
     }
+    };
+    if (parts5 == 1) trace_part(0);
+    else {
+        for (unsigned p = 0; p < parts5; ++p) pool5.emplace_back(trace_part, p);
+        for (auto& t : pool5) t.join();
+    }
+    }
+    {
+        size_t total = 0;
+        for (auto& pc : part_caps) total += pc.size();
+        T.caps.clear();
+        T.caps.reserve(total + 8);
+        for (unsigned part = 0; part < parts5; ++part) {
+            const uint32_t base = (uint32_t)(T.caps.size() / 4);
+            const uint32_t n0 = part_first[part], n1 = part_first[part + 1];
+            for (uint32_t i = std::max(n0, 1u); i < n1; ++i) T.nodes[i].cap_off += base;
+            T.caps.insert(T.caps.end(), part_caps[part].begin(), part_caps[part].end());
+        }
+    }
     T.caps.resize(T.caps.size() + 8, 0.0);
+    tm.lap("5 caps traced");
 }
 
 cudaStream_t pick(twg_ctx* c, void* stream) { return stream ? (cudaStream_t)stream : c->streams[0]; }
