@@ -174,33 +174,36 @@ struct Nearest {
     tw::V3 pt_deg;
 };
 
-// Exact nearest facet (nearest_facet_recursive, mesh_AABB.cpp:418-480)
+// Exact nearest facet (nearest_facet_recursive, mesh_AABB.cpp:418-480). Boxes are pruned with the conservative FP32 lower
+// bound of the box distance (never larger than the true distance, so no subtree that could hold a nearer facet is skipped;
+// the reference prunes with the double box distance, visits a subset of these boxes and finds the same minimum).
 __device__ __forceinline__ void nearest_facet(const SurfaceView& S, tw::V3 p, Nearest& best, const NodePair* top, uint32_t topN) {
     uint32_t stack[32];
-    double dstack[32];
+    float dstack[32];
+    const PointF q = bracket(p);
     int sp = 0;
     uint32_t node = 1;
     const uint32_t leaf0 = S.nLeafP;
     for (;;) {
         NodePair np = (node < topN) ? top[node] : load_pair(S.pairs + node);
-        const double dl = box_d2(p.x, p.y, p.z, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
-        const double dr = box_d2(p.x, p.y, p.z, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
+        const float dl = box_d2_lb(q, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
+        const float dr = box_d2_lb(q, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
         const uint32_t cl = 2u * node;
         if (cl >= leaf0) {
             const bool lfirst = dl <= dr;
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const bool left = (k == 0) ? lfirst : !lfirst;
-                const double db = left ? dl : dr;
+                const float db = left ? dl : dr;
                 const uint32_t pos = (left ? cl : cl + 1u) - leaf0;
-                if (db <= best.d2 * kSlack && pos < S.nF) {  // padding leaves (pos >= nF) have empty boxes
+                if ((double)db <= best.d2 * kSlack && pos < S.nF) {  // padding leaves (pos >= nF) have empty boxes
                     double s, t; tw::V3 nd; bool deg;
                     const double d2 = facet_d2(S, pos, p, s, t, nd, deg);
                     if (d2 < best.d2) { best.d2 = d2; best.s = s; best.t = t; best.pos = pos; best.deg = deg; best.pt_deg = nd; }
                 }
             }
         } else {
-            const bool hl = (dl <= best.d2 * kSlack) && (dl < 1e300), hr = (dr <= best.d2 * kSlack) && (dr < 1e300);
+            const bool hl = ((double)dl <= best.d2 * kSlack) && (dl < 1e30f), hr = ((double)dr <= best.d2 * kSlack) && (dr < 1e30f);
             if (hl && hr) {
                 const bool lnear = dl <= dr;
                 stack[sp] = lnear ? cl + 1u : cl;
@@ -215,7 +218,7 @@ __device__ __forceinline__ void nearest_facet(const SurfaceView& S, tw::V3 p, Ne
         for (;;) {
             if (sp == 0) return;
             --sp;
-            if (dstack[sp] <= best.d2 * kSlack) { node = stack[sp]; break; }
+            if ((double)dstack[sp] <= best.d2 * kSlack) { node = stack[sp]; break; }
         }
     }
 }
