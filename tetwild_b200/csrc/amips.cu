@@ -158,7 +158,7 @@ __device__ __forceinline__ void gather_vertex(const double* __restrict__ V, int3
 }
 
 // calTetQuality_AMIPS (LocalOperations.cpp:862-884)
-__global__ void __launch_bounds__(256) amips_quality_kernel(const double* __restrict__ V, const int4* __restrict__ tets, uint64_t nT,
+__global__ void __launch_bounds__(256, 3) amips_quality_kernel(const double* __restrict__ V, const int4* __restrict__ tets, uint64_t nT,
                                                             double* __restrict__ slim) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nT; i += (uint64_t)gridDim.x * blockDim.x) {
         const int4 t = __ldg(tets + i);

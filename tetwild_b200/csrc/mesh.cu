@@ -83,7 +83,7 @@ __device__ __forceinline__ void load_tet(const double* __restrict__ V, int4 t, d
 
 // calTetQuality_AMIPS over the resident mesh (LocalOperations.cpp:862-884); t_ids == NULL: tets 0..n-1.
 // A removed tet (negative first index) gives MAX_ENERGY: the reference never evaluates those (t_is_removed).
-__global__ void __launch_bounds__(256) mesh_quality_kernel(const double* __restrict__ V, const int4* __restrict__ T, const int32_t* __restrict__ t_ids,
+__global__ void __launch_bounds__(256, 3) mesh_quality_kernel(const double* __restrict__ V, const int4* __restrict__ T, const int32_t* __restrict__ t_ids,
                                                            uint64_t n, double* __restrict__ slim) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const int4 t = __ldg(T + (t_ids ? (uint64_t)__ldg(t_ids + i) : i));
