@@ -780,19 +780,33 @@ int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, do
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    TWG_TRY(twg_ensure_scratch(c, 0, up(n * 72) + up(n)));
-    char* base = (char*)c->dscratch[0];
-    cudaStream_t st = c->streams[0];
-    const bool small = n <= 4096;  // the faces of one local operation: stage through pinned slabs (pageable copies cost ~10 us each)
-    if (small) {
+    if (n <= 4096) {  // the faces of one local operation: pinned slabs, one copy each way (pageable copies cost ~10 us each)
+        TWG_TRY(twg_ensure_scratch(c, 0, up(n * 72) + up(n)));
         TWG_TRY(twg_ensure_pinned(c, up(n * 72), up(n)));
+        char* base = (char*)c->dscratch[0];
+        cudaStream_t st = c->streams[0];
         memcpy(c->pin_in[0], tris, n * 72);
+        TWG_CUDA(c, cudaMemcpyAsync(base, c->pin_in[0], n * 72, cudaMemcpyHostToDevice, st));
+        TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)base, n, sd, eps2, flags, (uint8_t*)(base + up(n * 72)), st));
+        TWG_CUDA(c, cudaMemcpyAsync(c->pin_out[0], base + up(n * 72), n, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+        memcpy(out, c->pin_out[0], n);
+        return 0;
     }
-    TWG_CUDA(c, cudaMemcpyAsync(base, small ? (const void*)c->pin_in[0] : (const void*)tris, n * 72, cudaMemcpyHostToDevice, st));
-    TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)base, n, sd, eps2, flags, (uint8_t*)(base + up(n * 72)), st));
-    TWG_CUDA(c, cudaMemcpyAsync(small ? (void*)c->pin_out[0] : (void*)out, base + up(n * 72), n, cudaMemcpyDeviceToHost, st));
-    TWG_CUDA(c, cudaStreamSynchronize(st));
-    if (small) memcpy(out, c->pin_out[0], n);
+    // large batches: 1 Mi-face chunks over the context's streams (bounds the scratch memory; smaller chunks cost more in kernel tails than the overlapped copy saves: 60.6 vs 67.5 M faces/s at 64 Ki)
+    const uint64_t chunk = 1ull << 20;
+    const uint64_t cmaxf = n < chunk ? n : chunk;
+    for (int k = 0; k < TWG_NUM_STREAMS; ++k) TWG_TRY(twg_ensure_scratch(c, k, up(cmaxf * 72) + up(cmaxf)));
+    int slot = 0;
+    for (uint64_t b = 0; b < n; b += chunk, slot = (slot + 1) % TWG_NUM_STREAMS) {
+        const uint64_t m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t st = c->streams[slot];
+        char* base = (char*)c->dscratch[slot];
+        TWG_CUDA(c, cudaMemcpyAsync(base, tris + 9 * b, m * 72, cudaMemcpyHostToDevice, st));
+        TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)base, m, sd, eps2, flags, (uint8_t*)(base + up(cmaxf * 72)), st));
+        TWG_CUDA(c, cudaMemcpyAsync(out + b, base + up(cmaxf * 72), m, cudaMemcpyDeviceToHost, st));
+    }
+    for (int k = 0; k < TWG_NUM_STREAMS; ++k) TWG_CUDA(c, cudaStreamSynchronize(c->streams[k]));
     return 0;
 }
 
