@@ -28,6 +28,7 @@ int main(int argc, char** argv) {
     build_host_tree(V.data(), (uint32_t)(V.size() / 3), F.data(), (uint32_t)(F.size() / 3), 64, T);
     auto fnv = [](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; unsigned long long h = 1469598103934665603ull; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } return h; };
     printf("checksums nodes %016llx caps %016llx tris %016llx\n", fnv(T.nodes.data(), T.nodes.size() * sizeof(WNode)), fnv(T.caps.data(), T.caps.size() * 8), fnv(T.tris.data(), T.tris.size() * 8));
+    printf("root cap points %u, children cap points %u %u\n", T.nodes[1].cap_cnt, T.nodes.size() > 3 ? T.nodes[2].cap_cnt : 0u, T.nodes.size() > 3 ? T.nodes[3].cap_cnt : 0u);
     printf("facets %zu nodes %zu cap points %zu total %.1f ms\n", F.size() / 3, T.nodes.size(), T.caps.size() / 4,
            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     return 0;
