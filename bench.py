@@ -289,13 +289,19 @@ def cpu_rate(part, n_full, threads, budget_s=8.0):
         V = synth.normalise_unit_diag(V)
         sd, eps, eps2 = synth.state_eps(1e-3)
         S = O.Surface(V, F)
+        if have_ref:  # the loop of LocalOperations.cpp:1046-1109 around the reference's own sampleTriangle, DistanceQuery.h and tree
+            RT = O.RefTree(V, F[S.order()])
+            fn = lambda T: RT.faces_out(T, sd, eps2, threads=threads)  # noqa: E731
+            kind, what = "reference", "reference sampleTriangle (Common.cpp:143-255) + DistanceQuery.h + mesh_AABB.cpp compiled unmodified, composed by the loop of LocalOperations.cpp:1046-1109 (oracle/ref_wrap.cpp)"
+        else:
+            fn = lambda T: S.faces_out(T, sd, eps2, threads=threads)  # noqa: E731
+            kind, what = "port", "oracle port of isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109)"
         T = synth.face_queries(V, F, 2000, FACE_EDGE, eps, seed=99)
-        t = time.perf_counter(); S.faces_out(T, sd, eps2, threads=threads); r0 = len(T) / (time.perf_counter() - t)
+        t = time.perf_counter(); fn(T); r0 = len(T) / (time.perf_counter() - t)
         m = int(min(n_full, max(2000, r0 * budget_s)))
         T = synth.face_queries(V, F, m, FACE_EDGE, eps, seed=3)
-        t = time.perf_counter(); S.faces_out(T, sd, eps2, threads=threads); dt = time.perf_counter() - t
-        return m / dt, "port", ("%d of %d faces, oracle port of isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109: sampleTriangle + "
-                                "facet_in_envelope_with_hint, first OUT sample stops the face), OpenMP over faces" % (m, n_full))
+        t = time.perf_counter(); fn(T); dt = time.perf_counter() - t
+        return m / dt, kind, "%d of %d faces, %s, first OUT sample stops the face, OpenMP over faces" % (m, n_full, what)
     if part == "winding":
         V, F = sphere_surface()
         WT = O.WindingTree(V, F)

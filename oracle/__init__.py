@@ -366,6 +366,15 @@ class RefTree:
         ref().ref_tree_nearest(self.h, _p(P, _dp), C.c_uint64(n), _p(f, _u32p), _p(q, _dp), _p(d, _dp), C.c_int(threads))
         return f, q, d
 
+    def faces_out(self, tris, sampling_dist, eps2, threads=1, degenerate_shortcut=True):
+        """isFaceOutEnvelop_sampling around the reference's own sampleTriangle / DistanceQuery.h / tree (ref_wrap.cpp)"""
+        T = _f64(tris).reshape(-1, 9)
+        n = len(T)
+        out, ns = np.empty(n, dtype=np.uint8), np.empty(n, dtype=np.uint64)
+        ref().ref_tree_faces_out(self.h, _p(T, _dp), C.c_uint64(n), C.c_double(sampling_dist), C.c_double(eps2),
+                                 C.c_int(1 if degenerate_shortcut else 0), _p(out, _u8p), _p(ns, _u64p), C.c_int(threads))
+        return out, ns
+
     def points_out(self, P, eps2, threads=1):
         P = _f64(P)
         n = len(P)

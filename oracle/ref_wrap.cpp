@@ -18,6 +18,9 @@
 #include <geogram/basic/geometry.h>
 #include <geogram/mesh/mesh.h>
 #include <tetwild/geogram/mesh_AABB.h>
+#include <tetwild/DistanceQuery.h>  /* the reference's own get_point_facet_nearest_point (DistanceQuery.h:20-39) */
+
+extern "C" int ora_triangle_is_degenerate(const double* p, const double* q, const double* r);  /* exact: CGAL's Triangle_3::is_degenerate on doubles */
 
 using std::pow;
 
@@ -131,6 +134,42 @@ void ref_tree_envelope_points_out(const ref_tree* t, const double* P, uint64_t n
         out[i] = d > eps2;
         if (facet) facet[i] = f;
         if (d2) d2[i] = d;
+    }
+}
+
+/* LocalOperations::isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109) restated around the reference's OWN
+ * sampleTriangle (Common.cpp:143-255), get_point_facet_nearest_point (DistanceQuery.h) and tree (mesh_AABB.cpp): degenerate
+ * face -> IN (:1048, exact predicate from oracle/predicates.c), samples visited from the middle, wrapping (:1078), previous
+ * facet as hint (:1080-1086), first OUT sample decides (:1088-1093). degenerate_shortcut = 0: the per-face body of
+ * Preprocess::isOutEnvelop (Preprocess.cpp:652-739), which samples every face and visits the samples in order. */
+void ref_tree_faces_out(const ref_tree* t, const double* tris9, uint64_t n, double sampling_dist, double eps2, int degenerate_shortcut,
+                        uint8_t* out, uint64_t* num_samples, int threads) {
+#pragma omp parallel num_threads(threads > 0 ? threads : 1)
+    {
+        std::vector<GEO::vec3> ps;
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t f = 0; f < (int64_t)n; ++f) {
+            const double* T = tris9 + 9 * f;
+            out[f] = 0;
+            if (num_samples) num_samples[f] = 0;
+            if (degenerate_shortcut && ora_triangle_is_degenerate(T, T + 3, T + 6)) continue;
+            std::array<GEO::vec3, 3> vs;
+            for (int i = 0; i < 3; ++i) vs[i] = GEO::vec3(T[3 * i], T[3 * i + 1], T[3 * i + 2]);
+            ps.clear();
+            tetwild::sampleTriangle(vs, ps, sampling_dist);
+            if (num_samples) num_samples[f] = ps.size();
+            GEO::vec3 nearest_point;
+            double sq_dist = std::numeric_limits<double>::max();
+            GEO::index_t prev_facet = GEO::NO_FACET;
+            const size_t ps_size = ps.size();
+            size_t cnt = 0;
+            for (size_t i = degenerate_shortcut ? ps_size / 2 : 0; cnt < ps_size; i = (i + 1) % ps_size, ++cnt) {
+                const GEO::vec3& current_point = ps[i];
+                if (prev_facet != GEO::NO_FACET) tetwild::get_point_facet_nearest_point(t->mesh, current_point, prev_facet, nearest_point, sq_dist);
+                if (sq_dist > eps2) t->aabb->facet_in_envelope_with_hint(current_point, eps2, prev_facet, nearest_point, sq_dist);
+                if (sq_dist > eps2) { out[f] = 1; break; }
+            }
+        }
     }
 }
 

@@ -8,6 +8,8 @@ stores inputs + outputs as JSON (hex floats, bit exact):
   sample_golden.json  sampleTriangle                                    src/tetwild/Common.cpp:143-255
   tree_golden.json    MeshFacetsAABBWithEps nearest_facet /             src/tetwild/geogram/mesh_AABB.cpp (whole file,
                       facet_in_envelope_with_hint                       over the geogram API shim of oracle/shim)
+  faces_golden.json   isFaceOutEnvelop_sampling decisions               src/tetwild/LocalOperations.cpp:1046-1109 composed from
+                      (+ the Preprocess::isOutEnvelop per-face body)    the reference's sampleTriangle, DistanceQuery.h and tree
 
 usage:  python tests/golden/make_golden.py
 """
@@ -67,7 +69,19 @@ def main():
                "surface": "synth.torus_knot(60, 12)", "eps2": float(eps2).hex(), "P": hx(P),
                "nearest_facet_original_ids": [int(x) for x in order[f]], "nearest_d2": hx(d), "nearest_pt": hx(q),
                "out": [int(x) for x in out]}, open(os.path.join(HERE, "tree_golden.json"), "w"))
-    for fn in ("amips_golden.json", "sample_golden.json", "tree_golden.json"):
+    # ---- isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109) and the Preprocess variant (Preprocess.cpp:652-739) composed
+    # from the reference's own sampleTriangle, DistanceQuery.h and tree (oracle/ref_wrap.cpp::ref_tree_faces_out)
+    T = synth.face_queries(V, F, 160, 0.01, eps, seed=404)                 # ~40 % out, ~64 samples each at sd / 4
+    T[::20] = np.array([0, 0, 5, 1, 1, 6, 2, 2, 7.0])                      # exactly collinear
+    sd = sd / 4
+    o1, n1 = RT.faces_out(T, sd, eps2)
+    o2, n2 = RT.faces_out(T, sd, eps2 * 0.64, degenerate_shortcut=False)
+    json.dump({"source": "reference sampleTriangle + DistanceQuery.h + mesh_AABB.cpp via oracle/_ref, loop of LocalOperations.cpp:1046-1109",
+               "surface": "synth.torus_knot(60, 12)", "sd": float(sd).hex(), "eps2": float(eps2).hex(), "tris": hx(T),
+               "out": [int(x) for x in o1], "num_samples": [int(x) for x in n1],
+               "preprocess_eps2": float(eps2 * 0.64).hex(), "preprocess_out": [int(x) for x in o2], "preprocess_num_samples": [int(x) for x in n2]},
+              open(os.path.join(HERE, "faces_golden.json"), "w"))
+    for fn in ("amips_golden.json", "sample_golden.json", "tree_golden.json", "faces_golden.json"):
         print(fn, os.path.getsize(os.path.join(HERE, fn)), "bytes")
 
 

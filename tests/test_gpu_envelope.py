@@ -121,6 +121,17 @@ def test_faces_out_exact(knot, ctx, oracle):
     assert len(Si.faces_out(np.zeros((0, 9)), 1e-3, 1e-6)) == 0
 
 
+def test_faces_golden(ctx):
+    """decisions recorded from the reference-built composition of LocalOperations.cpp:1046-1109 (tests/golden/faces_golden.json)"""
+    g = load_golden("faces_golden.json")
+    V, F = synth.torus_knot(60, 12)
+    S = tw.Surface(ctx, V, F)
+    T = unhex(g["tris"], (-1, 9))
+    sd = float.fromhex(g["sd"])
+    assert list(S.faces_out(T, sd, float.fromhex(g["eps2"]))) == g["out"]
+    assert list(S.faces_out(T, sd, float.fromhex(g["preprocess_eps2"]), degenerate_shortcut=False)) == g["preprocess_out"]
+
+
 def test_preprocess_face_test_has_no_degenerate_shortcut(knot, oracle):
     """Preprocess::isOutEnvelop (Preprocess.cpp:643-747) samples every face of the candidate set, degenerate or not;
     LocalOperations::isFaceOutEnvelop_sampling returns IN for a degenerate face (:1048)."""

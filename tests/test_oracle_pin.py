@@ -93,6 +93,21 @@ def test_tree_golden(oracle):
     assert 0.2 < out.mean() < 0.8
 
 
+def test_faces_golden(oracle):
+    """isFaceOutEnvelop_sampling decisions and sample counts recorded from the reference-built composition
+    (tests/golden/make_golden.py); survives where /root/reference does not exist."""
+    g = load_golden("faces_golden.json")
+    V, F = synth.torus_knot(60, 12)
+    S = oracle.Surface(V, F)
+    T = unhex(g["tris"], (-1, 9))
+    sd = float.fromhex(g["sd"])
+    out, ns = S.faces_out(T, sd, float.fromhex(g["eps2"]), threads=2)
+    assert list(out) == g["out"] and [int(x) for x in ns] == g["num_samples"] and 0.2 < out.mean() < 0.8
+    out2, ns2 = S.faces_out(T, sd, float.fromhex(g["preprocess_eps2"]), threads=2, degenerate_shortcut=False)
+    assert list(out2) == g["preprocess_out"] and [int(x) for x in ns2] == g["preprocess_num_samples"]
+    assert not out[::20].any() and ns[0] == 0 and ns2[0] > 0        # the collinear faces: shortcut vs sampled
+
+
 def test_envelope_known_answers(oracle):
     V, F = synth.icosphere(2)
     S = oracle.Surface(V, F)
@@ -177,6 +192,23 @@ def test_sampling_vs_reference(oracle):
             tri = np.round(tri * 100) / 100
         sd = 1e-3 if it % 2 else 2.5e-3
         assert np.array_equal(oracle.sample_triangle(tri, sd), oracle.ref_sample_triangle(tri, sd))
+
+
+def test_faces_vs_reference(oracle):
+    """the oracle's face test against the loop of LocalOperations.cpp:1046-1109 composed from the reference's own
+    sampleTriangle, DistanceQuery.h and mesh_AABB.cpp (oracle/ref_wrap.cpp::ref_tree_faces_out)"""
+    _need_ref(oracle)
+    V, F = synth.icosphere(4)
+    V = synth.normalise_unit_diag(V)
+    S = oracle.Surface(V, F)
+    RT = oracle.RefTree(V, F[S.order()])
+    sd, eps, eps2 = synth.state_eps(2e-3)
+    T = synth.face_queries(V, F, 1500, 0.03, eps, seed=6)
+    T[::37] = np.array([0, 0, 5, 1, 1, 6, 2, 2, 7.0])
+    for shortcut, e2 in ((True, eps2), (False, eps2 * 0.64)):
+        a, na = S.faces_out(T, sd, e2, threads=4, degenerate_shortcut=shortcut)
+        b, nb = RT.faces_out(T, sd, e2, threads=4, degenerate_shortcut=shortcut)
+        assert np.array_equal(a, b) and np.array_equal(na, nb) and 0.05 < a.mean() < 0.95
 
 
 def test_tree_vs_reference(oracle):
