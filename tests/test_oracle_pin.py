@@ -223,3 +223,33 @@ def test_tree_vs_reference(oracle):
     f2, q2, d2 = RT.nearest(P, threads=4)
     assert np.array_equal(d1, d2) and np.array_equal(q1, q2) and np.array_equal(f1, order[f2])
     assert np.array_equal(S.points_out(P, eps2, threads=4), RT.points_out(P, eps2, threads=4)[0])
+
+
+def test_boundary_mesh_vs_reference(oracle):
+    """isPointOutBoundaryEnvelop (LocalOperations.cpp:1111-1121) runs the same tree over the BOUNDARY mesh, whose facets
+    are edges stored as degenerate triangles (v1, v2, v2) (Preprocess.cpp:192-197): the oracle against the reference's
+    mesh_AABB.cpp on such a mesh (the degenerate branch of the leaf distance is the oracle's restatement on both sides)."""
+    _need_ref(oracle)
+    V, F = synth.uv_sphere(40, 40, noise=0.0)
+    keep = V[F.astype(np.int64)].mean(1)[:, 2] > 0.05
+    Fo = F[keep].astype(np.int64)                                  # open cap: its boundary is a ring of edges
+    e = np.concatenate([Fo[:, [0, 1]], Fo[:, [1, 2]], Fo[:, [2, 0]]])
+    key = np.sort(e, 1)
+    uniq, cnt = np.unique(key, axis=0, return_counts=True)
+    be = uniq[cnt == 1]
+    assert len(be) > 20
+    B = np.stack([be[:, 0], be[:, 1], be[:, 1]], 1).astype(np.uint32)
+    S = oracle.Surface(V, B)
+    order = S.order()
+    RT = oracle.RefTree(V, B[order])
+    rng = np.random.default_rng(3)
+    mid = 0.5 * (V[be[:, 0]] + V[be[:, 1]])
+    P = np.concatenate([mid[rng.integers(0, len(mid), 3000)] + rng.normal(0, 2e-3, (3000, 3)), rng.uniform(-0.6, 0.6, (2000, 3)), V[be[:200, 0]]])
+    f1, q1, d1 = S.nearest(P, threads=4)
+    f2, q2, d2 = RT.nearest(P, threads=4)
+    # d2 and the nearest point agree bit for bit; the facet may differ where two boundary edges share the nearest vertex
+    # (the oracle keeps the minimum over all facets, the reference the first it meets within rounding)
+    assert np.array_equal(d1, d2) and np.array_equal(q1, q2)
+    eps2 = (1.5e-3) ** 2
+    a, b = S.points_out(P, eps2, threads=4), RT.points_out(P, eps2, threads=4)[0]
+    assert np.array_equal(a, b) and 0.1 < a.mean() < 0.9
