@@ -5,13 +5,15 @@
 // (src/tetwild/VertexSmoother.cpp:627-702) and getNewEnergy (:544-625). Math: tw_math.cuh::amips_eval.
 //
 // Kernels
-//   amips_soa_kernel     flat SoA, one thread per VEC tets, 128-bit streaming loads of the 12 coordinate arrays,
-//                        E written coalesced, J3/H9 (AoS per tet, as the reference lays them out) transposed
-//                        through shared memory so that global stores are full 128-bit coalesced.
-//                        HBM-bound: 96 B in + 8/32/104 B out per tet.
+//   amips_soa_tma_kernel flat SoA E+J+H over full 256-tet tiles: two coalesced loads per coordinate array, J3/H9 rows (AoS per
+//                        tet, as the reference lays them out) written conflict-free into shared memory and stored by TMA
+//                        bulk shared->global copies. HBM-bound: 96 B in + 104 B out per tet (0.93 of the copy peak).
+//   amips_soa_kernel     the generic form (energy only, ragged tails, unaligned buffers): 128-bit streaming loads, J3/H9
+//                        transposed through shared memory and copied out with 128-bit stores.
 //   amips_quality_kernel indexed gather (int4 tet load + 4 vertex gathers), exact orientation gate.
-//   amips_ring_kernel    one warp per one-ring group, lanes over member tets, coalesced index loads, shuffle
-//                        reduction of the 13 outputs, lane 0 stores. FP64-pipe-bound.
+//   amips_ring_kernel    one warp per one-ring, lanes over member tets, software-pipelined over the warp's rings
+//                        (index chain of later rings in flight), 10 sums reduced through a shared-memory transpose.
+//                        Gather-latency bound.
 #include "common.cuh"
 
 namespace {
@@ -336,7 +338,7 @@ inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 int launch_soa(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, double* dH9, uint64_t n, cudaStream_t st) {
     if (n == 0) return 0;
     SoaArgs a;
-    bool vec = (n % 2 == 0) || true;
+    bool vec = true;  // 128-bit / TMA paths need 16-byte aligned arrays (checked below); odd n is handled by the tail code
     for (int k = 0; k < 12; ++k) { a.T[k] = dT[k]; vec = vec && aligned16(dT[k]); }
     a.E = dE; a.J3 = dJ3; a.H9 = dH9; a.n = n;
     vec = vec && (!dE || aligned16(dE)) && (!dJ3 || aligned16(dJ3)) && (!dH9 || aligned16(dH9));

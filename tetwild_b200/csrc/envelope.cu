@@ -3,14 +3,16 @@
 // Replaces LocalOperations::isPointOutEnvelop / isFaceOutEnvelop_sampling (src/tetwild/LocalOperations.cpp:1034-1109)
 // and the tree queries behind them (src/tetwild/geogram/mesh_AABB.cpp:381-548).
 //
-// Kernels
-//   env_points_kernel   one thread per query point, stack traversal of the implicit heap, early exit at the first
-//                       facet within eps. The top kTopNodes pair records are staged once per CTA into shared
-//                       memory by ONE 1-D bulk async copy (TMA, cp.async.bulk + mbarrier).
-//   nearest_kernel      same traversal without the eps cut (nearest facet / point / d2).
-//   env_faces_kernel    one warp per candidate face: sampleTriangle runs (sampling.cuh) are dealt to the lanes, each
-//                       lane walks its run sample by sample carrying the previous facet as a hint exactly like the
-//                       reference (:1080-1086); the first OUT sample raises a warp-shared flag and the warp stops.
+// Kernels (details above each one)
+//   env_points_kernel   persistent warps over groups of Morton-sorted queries: warp-cooperative group frontier, per-lane
+//                       8-wide conservative FP32 steps, parked leaf tests run in rounds, early exit at the first facet
+//                       within eps. The top kTopNodes pair records are staged once per CTA into shared memory by ONE 1-D
+//                       bulk async copy (TMA, cp.async.bulk + mbarrier).
+//   nearest_kernel      exact nearest facet / point / d2: best-first binary descent per lane, previous facet as first
+//                       bound, FP32 box bounds, dynamic work claiming.
+//   env_faces_kernel    one warp per candidate face: sampleTriangle's runs (sampling.cuh) flattened into equal chunks per
+//                       lane, one candidate-facet collection per face, SCAN / FETCH / LEAF stage rounds, previous facet
+//                       as hint like the reference (:1080-1086); the first OUT sample stops the warp.
 #include "surface.cuh"
 #include "sampling.cuh"
 
