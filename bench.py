@@ -679,7 +679,8 @@ def run_gpu(args, parts):
         ach = ALG_BYTES[part] * n / (kms * 1e-3) / 1e9
         res["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                            "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_unit": ALG_BYTES[part],
-                           "fp64_dfma_peak_tflops_measured_in_run": fp64_peak, "copy_gbs_measured_in_run": copy_gbs}
+                           "fp64_dfma_peak_tflops_measured_in_run": fp64_peak, "copy_gbs_measured_in_run": copy_gbs,
+                           "kernel_ms_scope": "CUDA events around ALL launches of one step on the launching stream (for the point / nearest / winding parts that includes the Morton sort of the batch), so `achieved` is a lower bound for the traversal kernel alone"}
         res["clocks"] = Clocks.summarise(clocks.window(*win)) if rank == 0 else None
         if rank == 0 and world == 1 and not args.no_cpu:
             v, kind, sample = cpu_rate(part, n, O.max_threads(), budget_s=args.cpu_budget)
