@@ -40,7 +40,8 @@ def harness():
     here = os.path.dirname(os.path.abspath(__file__))
     out = os.path.join(here, "_build", "libhost_harness.so")
     src = os.path.join(here, "host_harness.cpp")
-    deps = [src, os.path.join(ROOT, "tetwild_b200", "csrc", "tw_math.cuh"), os.path.join(ROOT, "tetwild_b200", "csrc", "sampling.cuh")]
+    deps = [src, os.path.join(ROOT, "tetwild_b200", "csrc", "tw_math.cuh"), os.path.join(ROOT, "tetwild_b200", "csrc", "sampling.cuh"),
+            os.path.join(ROOT, "tetwild_b200", "csrc", "winding_math.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -49,6 +50,8 @@ def harness():
     H.hh_tri_sqdist.restype = C.c_double
     H.hh_sample_triangle.restype = C.c_uint64
     H.hh_amips_energy.restype = C.c_double
+    H.hh_angle_sum.restype = C.c_double
+    H.hh_norm3.restype = C.c_double
     return H
 
 

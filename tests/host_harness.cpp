@@ -7,8 +7,33 @@
 #include <cstring>
 #include "../tetwild_b200/csrc/tw_math.cuh"
 #include "../tetwild_b200/csrc/sampling.cuh"
+#include "../tetwild_b200/csrc/winding_math.cuh"
 
 extern "C" {
+
+// running sum of atan2(y_k, x_k) through the product's complex-product accumulator (winding_math.cuh::Angle), renormalised
+// every `tile` factors like the kernel does per staged tile
+double hh_angle_sum(const double* x, const double* y, const uint8_t* skip, uint64_t n, int tile, int* k_out) {
+    tww::Angle a;
+    a.init();
+    for (uint64_t i = 0; i < n; ++i) {
+        a.mul(x[i], y[i], skip && skip[i]);
+        if ((i + 1) % (uint64_t)tile == 0) a.renorm();
+    }
+    a.renorm();
+    if (k_out) *k_out = a.k;
+    return a.total();
+}
+double hh_norm3(double x, double y, double z) { return tww::norm3(x, y, z); }
+// one Van Oosterom-Strackee factor (x + i y) of triangle (a, b, c) seen from p, with the kernel's arithmetic
+void hh_solid_angle_factor(const double* p, const double* A, const double* B, const double* C, double* xy) {
+    const double ax = A[0] - p[0], ay = A[1] - p[1], az = A[2] - p[2];
+    const double bx = B[0] - p[0], by = B[1] - p[1], bz = B[2] - p[2];
+    const double cx = C[0] - p[0], cy = C[1] - p[1], cz = C[2] - p[2];
+    const double la = tww::norm3(ax, ay, az), lb = tww::norm3(bx, by, bz), lc = tww::norm3(cx, cy, cz);
+    xy[1] = ax * (by * cz - bz * cy) + bx * (cy * az - cz * ay) + cx * (ay * bz - az * by);
+    xy[0] = la * lb * lc + (bx * cx + by * cy + bz * cz) * la + (cx * ax + cy * ay + cz * az) * lb + (ax * bx + ay * by + az * bz) * lc;
+}
 
 void hh_amips_ejh(const double* T12, double* E, double* J3, double* H9) {
     tw::Amips r;

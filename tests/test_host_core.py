@@ -135,3 +135,64 @@ def test_oracle_dihedral_known_answers(oracle):
     a, b = oracle.tet_dihedral(Vg, Tg)
     a2, b2 = oracle.tet_dihedral(Vg * 37.0 + 5.0, Tg)
     assert np.abs(a - a2).max() < 1e-9 and np.abs(b - b2).max() < 1e-9 and (a > 0).all() and (b < np.pi).all()
+
+
+def _angle_sum(harness, x, y, skip=None, tile=32):
+    x, y = np.ascontiguousarray(x, dtype=np.float64), np.ascontiguousarray(y, dtype=np.float64)
+    k = C.c_int(0)
+    sk = np.ascontiguousarray(skip, dtype=np.uint8) if skip is not None else None
+    v = harness.hh_angle_sum(P(x), P(y), sk.ctypes.data_as(C.POINTER(C.c_uint8)) if sk is not None else None, C.c_uint64(len(x)), C.c_int(tile), C.byref(k))
+    return v, k.value
+
+
+def test_winding_angle_accumulator(harness):
+    """The winding kernel never evaluates atan2 per triangle: sum_k atan2(y_k, x_k) = arg(prod (x_k + i y_k)) + 2 pi K with K
+    kept by branch-free sign-bit bookkeeping (winding_math.cuh::Angle). Same source, on the host: random factor streams of
+    wildly different magnitudes, long one-directional runs (K large), factors at +-pi, zero factors and chain starts."""
+    import math
+    rng = np.random.default_rng(17)
+    for it in range(300):
+        n = int(rng.integers(1, 400))
+        th = rng.uniform(-math.pi, math.pi, n) * rng.choice([1.0, 0.3, 0.02])
+        if it % 5 == 0:
+            th = np.abs(th)                                   # only counter-clockwise: K grows
+        if it % 7 == 0:
+            th = -np.abs(th)
+        mag = 10.0 ** rng.uniform(-15, 15, n)
+        x, y = mag * np.cos(th), mag * np.sin(th)
+        skip = (rng.random(n) < 0.05).astype(np.uint8)
+        if it % 3 == 0:
+            zi = rng.integers(0, n, max(1, n // 20))
+            x[zi] = 0.0; y[zi] = 0.0                          # atan2(0, 0) = 0 in the reference
+        ref = math.fsum(math.atan2(b, a) for a, b, s in zip(x, y, skip) if not s)
+        got, K = _angle_sum(harness, x, y, skip, tile=int(rng.choice([1, 7, 32])))
+        assert abs(got - ref) <= 1e-13 * max(1.0, n), (it, got, ref, K)
+    # factors exactly on the negative real axis: atan2(+0, -1) = +pi, atan2(-0, -1) = -pi
+    for y0, want in ((0.0, math.pi), (-0.0, -math.pi)):
+        got, K = _angle_sum(harness, [-1.0], [y0])
+        assert got == want
+    got, K = _angle_sum(harness, [-1.0] * 6, [0.0] * 6)          # six half turns = 6 pi
+    assert abs(got - 6 * math.pi) < 1e-14
+    got, K = _angle_sum(harness, [-2.0, -3.0], [1e-300, -1e-300])  # just short of +pi, then just short of -pi: total ~ 0
+    assert abs(got) < 1e-290 or abs(got) < 1e-15
+
+
+def test_winding_norm_and_closed_surface(harness):
+    """|v| through one third-order correction of a 22-bit reciprocal-root seed is correctly rounded to ~1 ulp, and the factors
+    of a closed surface add up to 4 pi (inside) / 0 (outside) through the accumulator."""
+    import math
+    rng = np.random.default_rng(5)
+    v = rng.normal(size=(20000, 3)) * 10.0 ** rng.uniform(-100, 100, (20000, 1))
+    got = np.array([harness.hh_norm3(C.c_double(a), C.c_double(b), C.c_double(c)) for a, b, c in v])
+    ref = np.sqrt((v.astype(np.longdouble) ** 2).sum(1)).astype(np.float64)
+    assert (np.abs(got - ref) <= 4e-16 * ref).all()
+    assert harness.hh_norm3(C.c_double(0), C.c_double(0), C.c_double(0)) > 0       # a query ON a vertex: tiny positive length
+    V, F = synth.icosphere(2)
+    for q, want in (([0.05, -0.1, 0.02], 4 * math.pi), ([0.9, 0.2, 0.1], 0.0), ([0.0, 0.0, 0.49], 4 * math.pi)):
+        xs, ys = [], []
+        for f in F.astype(np.int64):
+            xy = np.empty(2)
+            harness.hh_solid_angle_factor(P(np.array(q, dtype=np.float64)), P(V[f[0]].copy()), P(V[f[1]].copy()), P(V[f[2]].copy()), P(xy))
+            xs.append(xy[0]); ys.append(xy[1])
+        got, K = _angle_sum(harness, xs, ys)
+        assert abs(2.0 * got - want) < 1e-11            # Omega = 2 atan2(y, x) per triangle

@@ -29,6 +29,7 @@
 #include <chrono>
 #include <thread>
 #include "common.cuh"
+#include "winding_math.cuh"
 
 namespace {
 
@@ -55,57 +56,8 @@ struct WView {
     uint32_t nF;
 };
 
-// |v| for the solid-angle terms. Hardware seed y0 ~ 1/sqrt(l2) (MUFU.RSQ64H, relative error < 2^-21) followed by ONE
-// third-order correction: with s = l2*y0 and e = 1 - s*y0 (exact to rounding through the fma), sqrt(l2) =
-// s*(1 + e/2 + 3e^2/8 + O(e^3)); the neglected term is < 2^-63 relative. 5 FP64 instructions after the seed, branch free
-// (CUDA's sqrt() adds a slow-path call per use; two Newton steps on the reciprocal root cost 8).
-// The 1e-300 folded into the sum of squares only matters for a query ON a vertex (length 0): the factor then degenerates
-// to a positive real.
-__device__ __forceinline__ double norm3(double x, double y, double z) {
-    const double l2 = fma(x, x, fma(y, y, fma(z, z, 1e-300)));
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(l2));
-    const double s = l2 * y0;
-    const double e = fma(-s, y0, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    return fma(s * e, p, s);
-}
-
-// Running sum of atan2(y_f, x_f) as arg(z) + 2 pi k, z = prod (x_f + i y_f) (see the header comment).
-// BRANCH FREE: the loop bodies that call mul() must stay straight-line code so that the compiler can interleave the
-// unrolled iterations (the complex product is a serial chain of dependent FP64 operations; everything else of the next
-// point overlaps it). Half planes are told apart by the SIGN BIT of Im z, exactly like atan2 treats signed zeros:
-// U = {sign clear, arg in [+0, pi]}, L = {sign set, arg in [-pi, -0]}. A counter-clockwise factor (sign of y clear,
-// angle in [0, pi]) that takes z from U to L went through the negative real axis (k += 1); a clockwise factor from L to U
-// went through it the other way (k -= 1); U<->L moves in the other pairings cross the POSITIVE axis and change nothing.
-// A sign of Im z that rounding gets "wrong" can only happen next to the negative axis (next to the positive axis both
-// products of zr*y + zi*x have the same sign), where arg + 2 pi k is continuous, so the bookkeeping stays exact.
-struct Angle {
-    double zr, zi;
-    int k;
-    __device__ __forceinline__ void init() { zr = 1.0; zi = 0.0; k = 0; }
-    // z *= (x + i y) * 2^-e, e = the larger binary exponent of x, y (integer pipe); skip = chain start / zero factor
-    __device__ __forceinline__ void mul(double x, double y, bool skip) {
-        const int e = max(__double2hiint(x) & 0x7ff00000, __double2hiint(y) & 0x7ff00000);
-        skip = skip || e == 0;       // x = y = 0 (atan2(0,0) = 0 in the reference) or no triangle here: multiply by 1
-        const double sc = __hiloint2double(0x7fe00000 - e, 0);
-        x *= sc; y *= sc;            // |x + i y| in [1, 2 sqrt 2)
-        x = skip ? 1.0 : x;
-        y = skip ? 0.0 : y;
-        const double nr = fma(zr, x, -(zi * y));
-        const double ni = fma(zr, y, zi * x);
-        const int hz = __double2hiint(zi), hn = __double2hiint(ni), hy = __double2hiint(y);
-        const int m = (hz ^ hn) & ~(hy ^ hz);  // sign bit: half plane changed AND the factor turns away from the old half plane
-        k += (m >> 31) & (2 * (hz >> 31) + 1);
-        zr = nr; zi = ni;
-    }
-    __device__ __forceinline__ void renorm() {  // after at most 32 factors: |z| < 2^49 -> back to [1, 2 sqrt 2)
-        const int e = max(__double2hiint(zr) & 0x7ff00000, __double2hiint(zi) & 0x7ff00000);
-        const double sc = __hiloint2double(0x7fe00000 - e, 0);
-        zr *= sc; zi *= sc;
-    }
-    __device__ __forceinline__ double total() const { return atan2(zi, zr) + 6.283185307179586476925 * (double)k; }
-};
+using tww::norm3;
+using tww::Angle;
 
 struct Stream {  // per-warp tile streamer
     unsigned char* buf;  // 2 stages of kStageBytes
@@ -149,7 +101,7 @@ __device__ __forceinline__ void eval_cap(const WView& W, const WNode& nd, double
             const double ab = ax * bx + ay * by + az * bz;
             const double y = ox * (ay * bz - az * by) + oy * (az * bx - ax * bz) + oz * (ax * by - ay * bx);
             const double x = lo * (la * lb + ab) + ob * la + oa * lb;
-            acc.mul(x, y, __double2hiint(v.y) != 0);  // flag 1.0 (integer test): the first point of a chain closes no triangle
+            acc.mul(x, y, tww::hi32(v.y) != 0);  // flag 1.0 (integer test): the first point of a chain closes no triangle
             ax = bx; ay = by; az = bz; la = lb; oa = ob;
         }
         acc.renorm();
