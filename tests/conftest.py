@@ -52,6 +52,7 @@ def harness():
     H.hh_amips_energy.restype = C.c_double
     H.hh_angle_sum.restype = C.c_double
     H.hh_norm3.restype = C.c_double
+    H.hh_box_d2_lb.restype = C.c_float
     return H
 
 

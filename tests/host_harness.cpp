@@ -25,6 +25,11 @@ double hh_angle_sum(const double* x, const double* y, const uint8_t* skip, uint6
     return a.total();
 }
 double hh_norm3(double x, double y, double z) { return tww::norm3(x, y, z); }
+// the conservative FP32 lower bound of the squared distance from a double point to a float box (tw_math.cuh)
+float hh_box_d2_lb(const double* p, const float* box6) {
+    const tw::PointF q = tw::bracket(tw::mk(p[0], p[1], p[2]));
+    return tw::box_d2_lb(q, box6[0], box6[1], box6[2], box6[3], box6[4], box6[5]);
+}
 // one Van Oosterom-Strackee factor (x + i y) of triangle (a, b, c) seen from p, with the kernel's arithmetic
 void hh_solid_angle_factor(const double* p, const double* A, const double* B, const double* C, double* xy) {
     const double ax = A[0] - p[0], ay = A[1] - p[1], az = A[2] - p[2];

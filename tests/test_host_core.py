@@ -196,3 +196,37 @@ def test_winding_norm_and_closed_surface(harness):
             xs.append(xy[0]); ys.append(xy[1])
         got, K = _angle_sum(harness, xs, ys)
         assert abs(2.0 * got - want) < 1e-11            # Omega = 2 atan2(y, x) per triangle
+
+
+def test_conservative_box_bound_is_rigorous(harness):
+    """Every traversal prunes with tw_math.cuh::box_d2_lb: it must NEVER exceed the true squared distance from the (double)
+    query to the (float) box, or a subtree holding a facet within eps could be skipped and a decision would flip. Checked
+    against exact rational arithmetic, at scales from 1e-6 to 1e6 and for points inside, on and barely outside boxes."""
+    from fractions import Fraction
+    rng = np.random.default_rng(23)
+    worst = 0.0
+    for it in range(6000):
+        scale = 10.0 ** rng.uniform(-6, 6)
+        lo = (rng.normal(size=3) * scale).astype(np.float32)
+        hi = (lo.astype(np.float64) + np.abs(rng.normal(size=3)) * scale * rng.choice([1.0, 1e-3, 0.0])).astype(np.float32)
+        hi = np.maximum(hi, lo)
+        k = it % 4
+        if k == 0:
+            p = rng.normal(size=3) * scale * 3
+        elif k == 1:
+            p = lo.astype(np.float64) + (hi.astype(np.float64) - lo.astype(np.float64)) * rng.uniform(0, 1, 3)      # inside
+        elif k == 2:
+            p = hi.astype(np.float64) * (1 + rng.choice([1e-16, 1e-12, 1e-8, 1e-4], 3))                            # barely outside
+        else:
+            p = lo.astype(np.float64) - np.abs(rng.normal(size=3)) * scale * rng.choice([1e-9, 1e-3, 1.0])
+        box = np.concatenate([lo, hi]).astype(np.float32)
+        lb = float(harness.hh_box_d2_lb(P(np.ascontiguousarray(p)), box.ctypes.data_as(C.POINTER(C.c_float))))
+        exact = Fraction(0)
+        for c in range(3):
+            d = max(Fraction(float(lo[c])) - Fraction(float(p[c])), Fraction(float(p[c])) - Fraction(float(hi[c])), Fraction(0))
+            exact += d * d
+        assert Fraction(lb) <= exact, (it, lb, float(exact))
+        coord = max(float(np.abs(p).max()), float(np.abs(box).max()))
+        if float(exact) > (1e-2 * coord) ** 2:   # separations well above float resolution: the bound is also tight
+            worst = max(worst, 1.0 - lb / float(exact))
+    assert worst < 1e-3

@@ -82,27 +82,10 @@ __device__ __forceinline__ double facet_d2(const SurfaceView& S, uint32_t pos, t
     return tw::tri_sqdist_degenerate(p, tv, near_deg);
 }
 
-// Conservative single-precision box test. The query point is bracketed by two floats (p_lo <= p <= p_hi), every
-// operation is rounded DOWN, so the result is a rigorous lower bound of the true squared distance from p to the
-// (outward-rounded) box -- and the box contains every facet below it. A subtree is therefore never skipped when it
-// holds a facet with d2 <= eps2 (thr = eps2 rounded UP to float); the bound merely admits a few more boxes than the
-// exact double test would (relative slack ~1e-7). FP32 runs at twice the FP64 rate on B200 and leaves the FP64
-// pipe to the leaf arithmetic, which must stay bit-identical to the reference.
-struct PointF {
-    float lx, ly, lz, hx, hy, hz;
-};
-__device__ __forceinline__ PointF bracket(tw::V3 p) {
-    PointF q;
-    q.lx = __double2float_rd(p.x); q.ly = __double2float_rd(p.y); q.lz = __double2float_rd(p.z);
-    q.hx = __double2float_ru(p.x); q.hy = __double2float_ru(p.y); q.hz = __double2float_ru(p.z);
-    return q;
-}
-__device__ __forceinline__ float box_d2_lb(const PointF& q, float lx, float ly, float lz, float hx, float hy, float hz) {
-    const float dx = fmaxf(fmaxf(__fsub_rd(lx, q.hx), __fsub_rd(q.lx, hx)), 0.0f);
-    const float dy = fmaxf(fmaxf(__fsub_rd(ly, q.hy), __fsub_rd(q.ly, hy)), 0.0f);
-    const float dz = fmaxf(fmaxf(__fsub_rd(lz, q.hz), __fsub_rd(q.lz, hz)), 0.0f);
-    return __fmaf_rd(dz, dz, __fmaf_rd(dy, dy, __fmul_rd(dx, dx)));
-}
+// Conservative single-precision box test: tw_math.cuh (host/device, so that the CPU tier can check its rigor)
+using tw::PointF;
+using tw::bracket;
+using tw::box_d2_lb;
 
 // Is some facet within sqrt(eps2) of p?  (facet_in_envelope_recursive, mesh_AABB.cpp:482-548: stop at the first
 // facet with d2 <= eps2, never enter a box farther than eps.)  Binary descent, one query per lane; used by the

@@ -61,6 +61,53 @@ TW_HD V3 vnormalize(V3 a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Conservative single-precision box test (used by every traversal of surface.cuh / envelope.cu).
+// The query point is bracketed by two floats (p_lo <= p <= p_hi), every operation is rounded DOWN, so the result is a
+// rigorous lower bound of the true squared distance from p to the (outward-rounded) float box -- and the box contains
+// every facet below it. A subtree is therefore never skipped when it holds a facet with d2 <= eps2 (thr = eps2 rounded
+// UP to float); the bound merely admits a few more boxes than the exact double test would (relative slack ~1e-7).
+// FP32 runs at twice the FP64 rate on B200 and leaves the FP64 pipe to the leaf arithmetic.
+// Host build: the same operations under fesetround (tests/test_host_core.py checks the bound against exact rationals).
+// ------------------------------------------------------------------------------------------------------------
+struct PointF {
+    float lx, ly, lz, hx, hy, hz;
+};
+#if defined(__CUDA_ARCH__)
+TW_HD float f_down(double x) { return __double2float_rd(x); }
+TW_HD float f_up(double x) { return __double2float_ru(x); }
+TW_HD float fsub_down(float a, float b) { return __fsub_rd(a, b); }
+TW_HD float fmul_down(float a, float b) { return __fmul_rd(a, b); }
+TW_HD float ffma_down(float a, float b, float c) { return __fmaf_rd(a, b, c); }
+#else
+}  // namespace tw
+#include <cfenv>
+namespace tw {
+struct RoundGuard {
+    int old;
+    explicit RoundGuard(int mode) : old(std::fegetround()) { std::fesetround(mode); }
+    ~RoundGuard() { std::fesetround(old); }
+};
+// (operands go through volatiles: the compiler does not know that the conversions / operations depend on the rounding mode)
+inline float f_down(double x) { RoundGuard g(FE_DOWNWARD); volatile double vx = x; volatile float r = (float)vx; return r; }
+inline float f_up(double x) { RoundGuard g(FE_UPWARD); volatile double vx = x; volatile float r = (float)vx; return r; }
+inline float fsub_down(float a, float b) { RoundGuard g(FE_DOWNWARD); volatile float va = a, vb = b; volatile float r = va - vb; return r; }
+inline float fmul_down(float a, float b) { RoundGuard g(FE_DOWNWARD); volatile float va = a, vb = b; volatile float r = va * vb; return r; }
+inline float ffma_down(float a, float b, float c) { RoundGuard g(FE_DOWNWARD); volatile float va = a, vb = b, vc = c; volatile float r = std::fmaf(va, vb, vc); return r; }
+#endif
+TW_HD PointF bracket(V3 p) {
+    PointF q;
+    q.lx = f_down(p.x); q.ly = f_down(p.y); q.lz = f_down(p.z);
+    q.hx = f_up(p.x); q.hy = f_up(p.y); q.hz = f_up(p.z);
+    return q;
+}
+TW_HD float box_d2_lb(const PointF& q, float lx, float ly, float lz, float hx, float hy, float hz) {
+    const float dx = fmaxf(fmaxf(fsub_down(lx, q.hx), fsub_down(q.lx, hx)), 0.0f);
+    const float dy = fmaxf(fmaxf(fsub_down(ly, q.hy), fsub_down(q.ly, hy)), 0.0f);
+    const float dz = fmaxf(fmaxf(fsub_down(lz, q.hz), fsub_down(q.lz, hz)), 0.0f);
+    return ffma_down(dz, dz, ffma_down(dy, dy, fmul_down(dx, dx)));
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Point-triangle squared distance: the 7-region minimisation of Q(s,t) = |V0 + s e0 + t e1 - p|^2 (D. Eberly).
 // This is the leaf routine of the reference tree (mesh_AABB.cpp:153-171 -> geogram point_triangle_squared_distance).
 // The query-independent terms are precomputed once per facet into a 128-byte record (TriRec) with the same
