@@ -44,3 +44,22 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in src and "from oracle" not in src and "tw_oracle.h" not in src and "liboracle" not in src, f
+
+
+def test_docs_name_only_declared_entry_points():
+    """INTEGRATION.md and DESIGN.md must not drift from the header: every twg_* name they mention is declared (wildcards like
+    twg_mesh_* and bracketed suffixes like twg_x[_dev] are expanded against the header)."""
+    syms = set(declared_symbols())
+    types = {"twg_ctx", "twg_surface", "twg_winding", "twg_mesh"}
+    for doc in ("INTEGRATION.md", "DESIGN.md", "README.md"):
+        txt = open(os.path.join(ROOT, doc)).read()
+        for m in re.finditer(r"\b(twg_[a-z0-9_]+)(\[(_[a-z]+)\])?(\*)?", txt):
+            name, opt, star = m.group(1), m.group(3), m.group(4)
+            if name in types or name.rstrip("_") in types:
+                continue
+            if star or name.endswith("_"):
+                assert any(s.startswith(name) for s in syms), "%s: nothing declared matches %s*" % (doc, name)
+                continue
+            assert name in syms or any(s.startswith(name + "_") for s in syms), "%s mentions %s, which include/tetwild_gpu.h does not declare" % (doc, name)
+            if opt:
+                assert name + opt in syms, "%s mentions %s%s, not declared" % (doc, name, opt)
