@@ -493,6 +493,29 @@ struct InoutFiltering {
             t_is_removed[i] = !keep[cnt++];
         }
     }
+    /* MeshRefinement::markInOut (MeshRefinement.cpp:592-624) and the twin inside outputMidResult (:1036-1068): the same
+     * centroids and W > 0.5 rule WITHOUT the flip-and-retry of filter(); writes a copy, t_is_removed itself is untouched */
+    static void markInOut(Context& ctx, const double* V, const std::vector<std::array<int, 4> >& tets, const std::vector<bool>& t_is_removed,
+                          std::vector<bool>& tmp_t_is_removed, const double* SV, uint32_t nSV, const uint32_t* SF, uint32_t nSF) {
+        tmp_t_is_removed = t_is_removed;
+        std::vector<double> C;
+        C.reserve(3 * tets.size());
+        for (size_t i = 0; i < tets.size(); ++i) {
+            if (tmp_t_is_removed[i]) continue;
+            for (int c = 0; c < 3; ++c) {
+                const double s = V[3 * (size_t)tets[i][0] + c] + V[3 * (size_t)tets[i][1] + c] + V[3 * (size_t)tets[i][2] + c] + V[3 * (size_t)tets[i][3] + c];
+                C.push_back(s / 4.0);
+            }
+        }
+        const uint64_t nC = C.size() / 3;
+        std::vector<uint8_t> keep(nC);
+        if (nC) ctx.check(twg_winding_number(ctx.handle(), SV, nSV, SF, nSF, C.data(), nC, nullptr, keep.data()));
+        size_t cnt = 0;
+        for (size_t i = 0; i < tets.size(); ++i) {
+            if (tmp_t_is_removed[i]) continue;
+            tmp_t_is_removed[i] = !keep[cnt++];
+        }
+    }
 };
 
 }  // namespace twg

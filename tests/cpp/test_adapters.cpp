@@ -392,6 +392,17 @@ int main() {
                 const bool expect_removed = (i == 5 || i == 17) ? true : !okeep[i];
                 EXPECT(removed[i] == expect_removed, "filter decision differs at tet %zu (pass %d)", i, pass);
             }
+            // MeshRefinement::markInOut (:592-624): same rule, no flip-and-retry, result in a copy
+            std::vector<bool> before(tt.size(), false), marked;
+            before[5] = before[17] = true;
+            twg::InoutFiltering::markInOut(ctx, TV.data(), tt, before, marked, geo_sf_mesh.vertices.xyz.data(), (uint32_t)nSV, Fq.data(), (uint32_t)nSF);
+            std::vector<double> Wd(tt.size());
+            ora_winding_direct(geo_sf_mesh.vertices.xyz.data(), (uint32_t)nSV, Fq.data(), (uint32_t)nSF, cen.data(), tt.size(), Wd.data(), 4);
+            EXPECT(before[5] && before[17] && !before[0], "markInOut must not touch t_is_removed");
+            for (size_t i = 0; i < tt.size(); ++i) {
+                const bool expect_removed = (i == 5 || i == 17) ? true : !(Wd[i] > 0.5);
+                EXPECT(marked[i] == expect_removed, "markInOut decision differs at tet %zu (pass %d)", i, pass);
+            }
         }
     }
 
