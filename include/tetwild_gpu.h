@@ -23,8 +23,15 @@
  *   - vertices are xyz-interleaved doubles, facet / tet indices are 32-bit, facet ids returned are in the CALLER's
  *     numbering (the library sorts facets internally, like mesh_reorder at mesh_AABB.cpp:368-370, but never
  *     mutates caller data).
- *   - one context = one device; calls on one context are serialised by the caller (the reference is single-threaded).
- *     Multi-GPU: one context per device, batches split by index range.
+ *   - calls on one context are serialised by the caller (the reference is single-threaded). _dev calls on DIFFERENT
+ *     caller streams may overlap on the device: every stream owns its sort scratch and work counters (a "lane"; at
+ *     most 13 caller streams are tracked, further ones recycle the least recently used lane after its work finished).
+ *     A _dev call takes at most 2^31-1 queries; the host entry points chunk any size.
+ *   - multi-GPU: twg_create_multi opens one context over several devices of this process. Surface and
+ *     winding handles made on it are replicated on every device; every host-buffer batch call splits [0, n) into
+ *     contiguous index ranges, one per device, each staged and evaluated by that device's own host thread, results
+ *     written straight into the caller's buffer. _dev entry points need the one-device handles
+ *     (twg_device_context / twg_surface_replica / twg_winding_replica). The resident tet mesh (twg_mesh) lives on device 0.
  */
 #ifndef TETWILD_GPU_H
 #define TETWILD_GPU_H
@@ -48,18 +55,31 @@ typedef struct twg_winding twg_winding;   /* S4: winding-number hierarchy over a
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
 int twg_create(twg_ctx** ctx, int device_id);
+/* one context over n_devices distinct devices (n_devices == 1 is twg_create). SURVEY.md 8(b): twg_create(ctx, device_ids, n) */
+int twg_create_multi(twg_ctx** ctx, const int* device_ids, int n_devices);
+int twg_num_devices(const twg_ctx* ctx);
+twg_ctx* twg_device_context(twg_ctx* ctx, int k);  /* the one-device context of device k (k = 0: ctx itself when single) */
 void twg_destroy(twg_ctx* ctx);
 const char* twg_last_error(const twg_ctx* ctx);
 int twg_device(const twg_ctx* ctx);
 int twg_synchronize(twg_ctx* ctx);
 uint64_t twg_launch_count(const twg_ctx* ctx);  /* kernels launched by this context so far */
 const char* twg_version(void);
+/* Tuning knobs, per context (defaults: environment variable TWG_<NAME> read once at twg_create). Names: env_group, env_policy,
+ * env_front, env_quorum, env_top, envelope_sort, sort_bits, chunk_points, ring_waves, winding_minb, winding_sort,
+ * winding_leaf, winding_device_build, amips_tma, nearest_mode, trace. Values are clamped to their valid range. */
+int twg_set_option(twg_ctx* ctx, const char* name, double value);
+int twg_get_option(const twg_ctx* ctx, const char* name, double* value);
+/* diagnostics: 0 = envelope queries that overflowed the traversal stack and were re-decided by the exact binary descent */
+#define TWG_COUNTER_ENV_STACK_OVERFLOW 0
+int twg_debug_counter(twg_ctx* ctx, int which, uint64_t* value);
 
 /* ---- S2: surface build (replaces MeshFacetsAABBWithEps::MeshFacetsAABBWithEps, mesh_AABB.cpp:356-379) ------------ */
 int twg_surface_create(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_surface** out);
 int twg_surface_create_dev(twg_ctx* ctx, const double* dV, uint32_t nV, const uint32_t* dF, uint32_t nF, twg_surface** out);
 void twg_surface_destroy(twg_surface* s);
 uint32_t twg_surface_num_facets(const twg_surface* s);
+twg_surface* twg_surface_replica(twg_surface* s, int k);  /* replica on device k of a multi-device context (k = 0: s itself when single) */
 
 /* a10/a12: out[i] = 1 iff min_f d2(P_i, f) > eps2
  * (isPointOutEnvelop LocalOperations.cpp:1034-1044; per-sample test of :1083-1093 via facet_in_envelope_with_hint) */
@@ -165,6 +185,7 @@ int twg_mesh_ring_energy(twg_mesh* m, const int32_t* t_ids, const uint64_t* grou
 /* F may contain repeated faces (InoutFiltering.cpp:99-100). */
 int twg_winding_create(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out);
 void twg_winding_destroy(twg_winding* w);
+twg_winding* twg_winding_replica(twg_winding* w, int k);
 /* W[i] and/or keep[i] = (W[i] > 0.5) for query i (either may be NULL) */
 int twg_winding_eval(twg_winding* w, const double* C, uint64_t nC, double* W, uint8_t* keep);
 int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* dW, uint8_t* dKeep, void* stream);

@@ -34,6 +34,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <cmath>
 #include <vector>
 
 #include "tetwild_gpu.h"
@@ -55,8 +56,15 @@ public:
         int rc = twg_create(&h_, device_id);
         if (rc != 0) throw Error(rc, "twg_create failed (no sm_100-class GPU or library built for another arch; there is no CPU fallback)");
     }
+    /* one context over several devices: handles are replicated, host-buffer batches are split by index range */
+    explicit Context(const std::vector<int>& device_ids) : h_(nullptr) {
+        int rc = twg_create_multi(&h_, device_ids.data(), (int)device_ids.size());
+        if (rc != 0) throw Error(rc, "twg_create_multi failed (a device is missing or not sm_100-class; there is no CPU fallback)");
+    }
     ~Context() { twg_destroy(h_); }
     twg_ctx* handle() const { return h_; }
+    int num_devices() const { return twg_num_devices(h_); }
+    void set_option(const char* name, double value) const { check(twg_set_option(h_, name, value)); }
     void check(int rc) const {
         if (rc != 0) throw Error(rc, std::string("libtetwild_gpu: ") + twg_last_error(h_));
     }
@@ -186,16 +194,29 @@ inline void energy_ispc(Context& ctx, const double* V1_x, const double* V1_y, co
     ctx.check(twg_amips_energy_soa(ctx.handle(), T, E, (uint64_t)(count < 0 ? 0 : count)));
 }
 
-/* State.cpp:36-41 (default --stage 1): the kernel parameters derived from the user's eps_rel and the bbox diagonal */
+/* State::State (State.cpp:24-41): the kernel parameters derived from the user's eps_rel, --stage and the bbox diagonal, with
+ * the reference's own expressions (eps_2 is compared bit for bit, so the threshold must be the same double):
+ *   sampling_dist = eps_input / stage;  eps = eps_input - sampling_dist / sqrt(3) * (stage + 1 - sub_stage);  eps_2 = eps * eps
+ * and the per-sub-stage growth of MeshRefinement.cpp:317-320,340-344:  eps += eps_delta;  eps_2 = eps * eps. */
 struct EnvelopeParams {
-    double eps, eps_2, sampling_dist;
-    static EnvelopeParams from_args(double bbox_diag, double eps_rel) {
+    double eps, eps_2, sampling_dist, eps_delta;
+    int stage, sub_stage;
+    static EnvelopeParams from_args(double bbox_diag, double eps_rel, int stage = 1, int sub_stage = 1) {
         EnvelopeParams e;
         const double eps_input = bbox_diag * eps_rel;
-        e.sampling_dist = eps_input;
-        e.eps = eps_input * (1.0 - 1.0 / 1.7320508075688772);  /* eps_input - eps_input/sqrt(3) */
-        e.eps_2 = e.eps * e.eps;
+        e.stage = stage;
+        e.sub_stage = sub_stage;
+        e.eps_delta = eps_input / stage / std::sqrt(3);                                   /* State.cpp:25 */
+        e.sampling_dist = eps_input / stage;                                              /* State.cpp:37 */
+        e.eps = eps_input - e.sampling_dist / std::sqrt(3) * (stage + 1 - sub_stage);     /* State.cpp:38 */
+        e.eps_2 = e.eps * e.eps;                                                          /* State.cpp:39 */
         return e;
+    }
+    /* MeshRefinement.cpp:317-320 / :340-344 */
+    void next_sub_stage() {
+        eps += eps_delta;
+        eps_2 = eps * eps;
+        ++sub_stage;
     }
 };
 

@@ -15,6 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 _REF = os.path.join(_HERE, "_ref", "libtetwild_ref.so")
+_REFQ = os.path.join(_HERE, "_ref", "libtetwild_ref_quad.so")
 
 MAX_ENERGY = 1e50
 NO_FACET = 0xFFFFFFFF
@@ -33,7 +34,8 @@ def build(force=False):
         for f in ("predicates.c", "amips.c", "envelope.c", "winding.c", "tw_oracle.h")
     ):
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
-    if os.path.isdir("/root/reference/src/tetwild") and (force or not os.path.exists(_REF)):
+    if os.path.isdir("/root/reference/src/tetwild") and (force or not os.path.exists(_REF) or not os.path.exists(_REFQ)
+                                                        or os.path.getmtime(os.path.join(_HERE, "ref_quad.cpp")) > os.path.getmtime(_REFQ)):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
 
 
@@ -323,6 +325,38 @@ def ref_amips_ejh_soa(T, threads=1, want=(True, True, True)):
     H = np.empty((n, 9)) if want[2] else None
     ref().ref_amips_ejh_soa(ptrs, _p(E, _dp), _p(J, _dp), _p(H, _dp), C.c_uint64(n), C.c_int(threads))
     return E, J, H
+
+
+_refq = None
+
+
+def quad_available():
+    return os.path.exists(_REFQ)
+
+
+def _quad(fn, T, threads):
+    """oracle/_ref/libtetwild_ref_quad.so (oracle/ref_quad.cpp): binary128 evaluations, results rounded to double"""
+    global _refq
+    if _refq is None:
+        if not os.path.exists(_REFQ):
+            raise RuntimeError("oracle/_ref/libtetwild_ref_quad.so not built (needs /root/reference; run oracle/ref_build.sh)")
+        _refq = C.CDLL(_REFQ)
+    T, ptrs = _soa_ptrs(T)
+    n = T.shape[1]
+    E, J, H = np.empty(n), np.empty((n, 3)), np.empty((n, 9))
+    getattr(_refq, fn)(ptrs, _p(E, _dp), _p(J, _dp), _p(H, _dp), C.c_uint64(n), C.c_int(threads))
+    return E, J, H
+
+
+def refq_amips_ejh_soa(T, threads=1):
+    """the reference's own text (LocalOperations.cpp:28-291) evaluated in IEEE binary128: the exact value of the
+    reference's expression as written, for the same double inputs"""
+    return _quad("refq_amips_ejh_soa", T, threads)
+
+
+def exactq_amips_ejh_soa(T, threads=1):
+    """the mathematical conformal AMIPS energy / gradient / Hessian (exact constants) in binary128"""
+    return _quad("exactq_amips_ejh_soa", T, threads)
 
 
 def ref_amips_ring_ejh(V, tets, group_off, center, t_ids=None, threads=1):

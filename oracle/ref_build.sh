@@ -26,3 +26,6 @@ $CC -O2 -fPIC -fopenmp -ffp-contract=off -std=gnu11 -I"$HERE" -c "$HERE/envelope
 $CC -O2 -fPIC -fopenmp -ffp-contract=off -std=gnu11 -I"$HERE" -c "$HERE/predicates.c" -o "$OUT/gen/predicates.o"
 $CXX -shared -fopenmp -o "$OUT/libtetwild_ref.so" "$OUT/gen/mesh_AABB.o" "$OUT/gen/ref_wrap.o" "$OUT/gen/envelope_leaf.o" "$OUT/gen/predicates.o" -lm
 echo "ref_build: built $OUT/libtetwild_ref.so"
+# (4) the same AMIPS text in IEEE binary128 (higher-precision truth for the 1e-9 question): oracle/ref_quad.cpp
+$CXX -O2 -fPIC -fopenmp -std=c++14 -w -I"$OUT/gen" -shared -o "$OUT/libtetwild_ref_quad.so" "$HERE/ref_quad.cpp" -lquadmath
+echo "ref_build: built $OUT/libtetwild_ref_quad.so"

@@ -1,5 +1,4 @@
 """GPU tier: winding-number kernels through the C ABI against the oracle. Decisions (W > 0.5) exact; W within 1e-10."""
-import os
 
 import numpy as np
 import pytest
@@ -26,22 +25,26 @@ def test_closed_sphere_known_answers(ctx, oracle):
     assert not retried and list(keep) == [1, 1, 0, 0]
 
 
-@pytest.mark.parametrize("tma,sort", [("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")])
-def test_vs_oracle_direct(ctx, oracle, tma, sort):
-    os.environ["TWG_WINDING_TMA"], os.environ["TWG_WINDING_SORT"] = tma, sort
-    try:
-        V, F = synth.uv_sphere(90, 90, noise=0.02, seed=3)
-        Q = synth.winding_queries(V, 30000, seed=8)
-        Wt = tw.Winding(ctx, V, F)
-        W, keep = Wt.eval(Q)
-        Wd = oracle.winding_direct(V, F, Q, threads=8)
-        assert np.abs(W - Wd).max() < 1e-10
-        assert np.array_equal(keep, (Wd > 0.5).astype(np.uint8))
-        assert 0.1 < keep.mean() < 0.6
-        st = Wt.stats()
-        assert st["triangles"] == len(F) and st["cap_segments"] > 0
-    finally:
-        os.environ.pop("TWG_WINDING_TMA"), os.environ.pop("TWG_WINDING_SORT")
+@pytest.mark.parametrize("sort,leaf,device_build", [(1, 64, 1), (0, 64, 1), (1, 16, 1), (1, 64, 0), (0, 256, 0)])
+def test_vs_oracle_direct(oracle, sort, leaf, device_build):
+    """query order (Morton-sorted or the caller's), leaf block size and where the hierarchy is built (device / host threads)
+    are per-context options (twg_set_option); none of them may change a result beyond rounding"""
+    c = tw.Context(0)
+    c.set_option("winding_sort", sort)
+    c.set_option("winding_leaf", leaf)
+    c.set_option("winding_device_build", device_build)
+    V, F = synth.uv_sphere(90, 90, noise=0.02, seed=3)
+    Q = synth.winding_queries(V, 30000, seed=8)
+    Wt = tw.Winding(c, V, F)
+    W, keep = Wt.eval(Q)
+    Wd = oracle.winding_direct(V, F, Q, threads=8)
+    assert np.abs(W - Wd).max() < 1e-10
+    assert np.array_equal(keep, (Wd > 0.5).astype(np.uint8))
+    assert 0.1 < keep.mean() < 0.6
+    st = Wt.stats()
+    assert st["triangles"] == len(F) and st["cap_segments"] > 0
+    Wt.close()
+    c.close()
 
 
 def test_open_and_soup(ctx, oracle):

@@ -1,0 +1,189 @@
+"""Ground truths that do not depend on any restatement (tests/golden/make_golden_truth.py): the reference's AMIPS text in IEEE
+binary128, exact-rational point-triangle distances, 40-digit mpmath winding numbers. The CPU tier checks the oracle and the
+product's host-compilable numeric core against them; the GPU tier checks the kernels through the C ABI.
+
+AMIPS criterion claimed: per tet and per tensor (E, J, H), max-norm error relative to the tensor's max-norm
+<= 1e-9 against the EXACT value of the reference's expression. The per-component bar of BASELINE.md section 3,
+|gpu - cpu| <= 1e-9 max(1, |cpu|), is not claimed: the reference's own double evaluation misses it against its own
+binary128 value (6 284 of 50 000 literal-C3 tets; 1 of 50 000 on the commensurate C3), because a component that is small
+against its tensor's norm carries the absolute error of the large ones.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, unhex
+from tetwild_b200 import synth
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def normwise(a, b):
+    n = len(b[0])
+    return [np.abs(a[k].reshape(n, -1) - b[k].reshape(n, -1)).max(1) / np.abs(b[k].reshape(n, -1)).max(1) for k in range(3)]
+
+
+def load_amips_truth():
+    g = load_golden("amips_truth_golden.json")
+    n = g["n"]
+    T = unhex(g["T_rows_12xn"], (12, n))
+    Q = (unhex(g["Eq"]), unhex(g["Jq"], (n, 3)), unhex(g["Hq"], (n, 9)))
+    X = (unhex(g["Ex"]), unhex(g["Jx"], (n, 3)), unhex(g["Hx"], (n, 9)))
+    R = (unhex(g["Er"]), unhex(g["Jr"], (n, 3)), unhex(g["Hr"], (n, 9)))
+    return T, Q, X, R, g["stats_50k"]
+
+
+def harness_ejh(harness, T):
+    T = np.ascontiguousarray(T)
+    n = T.shape[1]
+    E, J, H = np.empty(n), np.empty((n, 3)), np.empty((n, 9))
+    harness.hh_amips_ejh_batch(P(T), C.c_uint64(n), P(E), P(J), P(H))
+    return E, J, H
+
+
+# ------------------------------------------------------------------------------------------------------- AMIPS
+def test_amips_closed_form_vs_binary128_truth_on_literal_c3(harness):
+    """Literal C3 (translation U(-10,10)^3, scale 1e-3..1e3): the closed form the kernels run stays within 1e-9 of the exact value
+    of the reference's expression, and is closer to it than the reference's own double evaluation (whose worst tets are the
+    first 100 of the fixture)."""
+    T, Q, X, R, stats = load_amips_truth()
+    G = harness_ejh(harness, T)
+    eg, er, ex = normwise(G, Q), normwise(R, Q), normwise(G, X)
+    for k in range(3):
+        assert eg[k].max() <= 1e-9, "closed form vs binary128 truth: %g" % eg[k].max()
+        assert eg[k].max() <= er[k].max()
+        assert ex[k].max() <= 1e-11
+    assert max(e.max() for e in er) > 1e-8          # the fixture does hold the tets that miss 1e-9 in the reference's own doubles
+    assert stats["reference_double_vs_its_binary128_value"]["tets_over_1e-9"] > 1000
+
+
+def test_amips_oracle_reference_text_is_what_the_fixture_says(oracle):
+    """where oracle/_ref exists: the committed Er / Eq are reproduced by the reference text compiled here (double and binary128)"""
+    if not (oracle.ref_available() and oracle.quad_available()):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    T, Q, X, R, _ = load_amips_truth()
+    R2 = oracle.ref_amips_ejh_soa(T)
+    Q2 = oracle.refq_amips_ejh_soa(T)
+    for k in range(3):
+        assert np.array_equal(R2[k], R[k])
+        assert np.array_equal(Q2[k], Q[k])
+
+
+def test_amips_full_literal_c3_sample(harness, oracle):
+    """the 50 k sample the fixture was drawn from, recomputed: zero tets over 1e-9 for the closed form, thousands for the
+    reference's double evaluation"""
+    if not (oracle.ref_available() and oracle.quad_available()):
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    T = synth.random_tets(50000, seed=7, trans_scales=False)
+    Q = oracle.refq_amips_ejh_soa(T, threads=4)
+    G = harness_ejh(harness, T)
+    R = oracle.ref_amips_ejh_soa(T, threads=4)
+    eg, er = normwise(G, Q), normwise(R, Q)
+    assert int(((eg[0] > 1e-9) | (eg[1] > 1e-9) | (eg[2] > 1e-9)).sum()) == 0
+    assert int(((er[0] > 1e-9) | (er[1] > 1e-9) | (er[2] > 1e-9)).sum()) > 1000
+    assert max(e.max() for e in eg) < 1e-9 < max(e.max() for e in er)
+
+
+@pytest.mark.gpu
+def test_gpu_amips_vs_binary128_truth(ctx):
+    T, Q, X, R, _ = load_amips_truth()
+    G = ctx.amips_ejh_soa(T)
+    eg, er = normwise(G, Q), normwise(R, Q)
+    for k in range(3):
+        assert eg[k].max() <= 1e-9 and eg[k].max() <= er[k].max()
+        assert normwise(G, X)[k].max() <= 1e-11
+
+
+@pytest.mark.gpu
+def test_gpu_amips_literal_c3_full_sample(ctx, oracle):
+    """the literal config 3 on the device: E, J, H of 200 k tets within 1e-9 of the binary128 value of the reference text"""
+    if not oracle.quad_available():
+        pytest.skip("oracle/_ref/libtetwild_ref_quad.so did not travel")
+    T = synth.random_tets(200000, seed=11, trans_scales=False)
+    G = ctx.amips_ejh_soa(T)
+    Q = oracle.refq_amips_ejh_soa(T, threads=oracle.max_threads())
+    R = oracle.ref_amips_ejh_soa(T, threads=oracle.max_threads())
+    eg, er = normwise(G, Q), normwise(R, Q)
+    assert max(e.max() for e in eg) <= 1e-9
+    assert max(e.max() for e in eg) <= max(e.max() for e in er)
+
+
+# ------------------------------------------------------------------------------------------------------- point-triangle
+def load_trisq():
+    g = load_golden("trisq_exact_golden.json")
+    n = g["n"]
+    return unhex(g["P"], (n, 3)), unhex(g["T"], (n, 3, 3)), unhex(g["d2"]), unhex(g["cond"])
+
+
+def trisq_scale(Pq, T, cond):
+    """error model of the routine (Eberly's 7-region algorithm as geogram runs it): it forms c = |V0 - p|^2 and cancels it
+    against terms of the same size, so the absolute error is a few ulps of the squared distance to the farthest vertex,
+    times the condition number a00 a11 / det of the 2x2 solve (1 / sin^2 of the corner angle: ~1 for ordinary facets, large for
+    needles -- a property of the reference's algorithm, reproduced bit for bit, not of this implementation); the segment branch
+    of degenerate facets forms the nearest point in absolute coordinates first, which adds ulp(|coordinates|) * distance"""
+    far2 = np.max(((T - Pq[:, None, :]) ** 2).sum(2), axis=1)
+    cmax = np.maximum(np.abs(T).max((1, 2)), np.abs(Pq).max(1))
+    return far2 * np.maximum(1.0, cond) + cmax * np.sqrt(far2)
+
+
+def test_point_triangle_distance_vs_exact_rationals(harness, oracle):
+    Pq, T, d2, cond = load_trisq()
+    sc = trisq_scale(Pq, T, cond)
+    assert (cond < 100).mean() > 0.7      # most cases are ordinary facets, where the bound is a few ulps of the scale
+    worst_h = worst_o = 0.0
+    for i in range(len(Pq)):
+        near = np.empty(3)
+        harness.hh_tri_sqdist.restype = C.c_double
+        dh = harness.hh_tri_sqdist(P(Pq[i]), P(np.ascontiguousarray(T[i, 0])), P(np.ascontiguousarray(T[i, 1])), P(np.ascontiguousarray(T[i, 2])), P(near))
+        do, no = oracle.point_triangle_sqdist(Pq[i], T[i, 0], T[i, 1], T[i, 2])
+        assert dh == do                                                       # product source == oracle restatement, bit for bit
+        worst_h = max(worst_h, abs(dh - d2[i]) / sc[i])
+        assert abs(dh - d2[i]) <= 64 * 2.0 ** -53 * sc[i], (i, dh, d2[i])
+        # the returned nearest point realises the distance
+        # the returned nearest point realises the distance
+        assert abs(((near - Pq[i]) ** 2).sum() - d2[i]) <= 256 * 2.0 ** -53 * sc[i]
+    assert worst_h < 64 * 2.0 ** -53
+
+
+@pytest.mark.gpu
+def test_gpu_point_triangle_distance_vs_exact_rationals(ctx):
+    """one-facet surfaces: twg_nearest is then the leaf routine alone"""
+    import tetwild_b200 as tw
+    Pq, T, d2, cond = load_trisq()
+    sc = trisq_scale(Pq, T, cond)
+    for i in range(0, len(Pq), 5):
+        S = tw.Surface(ctx, np.ascontiguousarray(T[i]), np.array([[0, 1, 2]], dtype=np.uint32))
+        f, q, d = S.nearest(Pq[i:i + 1])
+        S.close()
+        assert abs(d[0] - d2[i]) <= 64 * 2.0 ** -53 * sc[i], (i, d[0], d2[i])
+
+
+# ------------------------------------------------------------------------------------------------------- winding
+def winding_cases():
+    g = load_golden("winding_mp_golden.json")
+    for c in g["cases"]:
+        yield c["name"], unhex(c["V"], (-1, 3)), np.array(c["F"], dtype=np.uint32).reshape(-1, 3), unhex(c["Q"], (-1, 3)), unhex(c["W"])
+
+
+def test_winding_oracle_vs_mpmath(oracle):
+    total = 0
+    for name, V, F, Q, W in winding_cases():
+        Wd = oracle.winding_direct(V, F, Q, threads=4)
+        Wt = oracle.WindingTree(V, F).eval(Q, threads=4)
+        assert np.abs(Wd - W).max() < 1e-12, name
+        assert np.abs(Wt - W).max() < 1e-12, name
+        total += len(Q)
+    assert total >= 2000
+
+
+@pytest.mark.gpu
+def test_gpu_winding_vs_mpmath(ctx):
+    import tetwild_b200 as tw
+    for name, V, F, Q, W in winding_cases():
+        Wg, keep = tw.Winding(ctx, V, F).eval(Q)
+        assert np.abs(Wg - W).max() < 1e-12, (name, np.abs(Wg - W).max())
+        clear = np.abs(W - 0.5) > 1e-9
+        assert np.array_equal(keep[clear], (W[clear] > 0.5).astype(np.uint8)), name

@@ -20,7 +20,7 @@ def tool():
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         os.makedirs(os.path.dirname(EXE), exist_ok=True)
         subprocess.check_call(["nvcc", "-ccbin", "/usr/bin/g++", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
-                               "-o", EXE, src, os.path.join(csrc, "ctx.cu"), os.path.join(csrc, "qsort.cu")], cwd=os.path.join(ROOT, "tools"))
+                               "-o", EXE, src, os.path.join(csrc, "ctx.cu"), os.path.join(csrc, "multi.cu"), os.path.join(csrc, "qsort.cu")], cwd=os.path.join(ROOT, "tools"))
     return EXE
 
 

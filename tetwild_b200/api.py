@@ -61,6 +61,16 @@ def load_library():
     L.twg_mesh_vertices_dev.restype = C.c_void_p
     L.twg_mesh_tets_dev.argtypes = [_vp]
     L.twg_mesh_tets_dev.restype = C.c_void_p
+    L.twg_device_context.argtypes = [_vp, C.c_int]
+    L.twg_device_context.restype = C.c_void_p
+    L.twg_surface_replica.argtypes = [_vp, C.c_int]
+    L.twg_surface_replica.restype = C.c_void_p
+    L.twg_winding_replica.argtypes = [_vp, C.c_int]
+    L.twg_winding_replica.restype = C.c_void_p
+    L.twg_num_devices.argtypes = [_vp]
+    L.twg_set_option.argtypes = [_vp, C.c_char_p, C.c_double]
+    L.twg_get_option.argtypes = [_vp, C.c_char_p, C.POINTER(C.c_double)]
+    L.twg_debug_counter.argtypes = [_vp, C.c_int, C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -78,16 +88,39 @@ def _dev(p):
 
 
 class Context:
-    """twg_ctx: one device."""
+    """twg_ctx: one device (device = int) or several devices of this process (device = sequence of ints, twg_create_multi:
+    handles are replicated on every device and host-buffer batches are split by index range)."""
 
     def __init__(self, device=0):
         self._L = load_library()
         h = C.c_void_p()
-        rc = self._L.twg_create(C.byref(h), C.c_int(device))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self._L.twg_create_multi(C.byref(h), ids, C.c_int(len(device)))
+        else:
+            rc = self._L.twg_create(C.byref(h), C.c_int(device))
         if rc != 0:
-            raise TetWildGPUError("twg_create(device=%d) failed with code %d (no sm_100-class GPU? there is no CPU fallback)" % (device, rc))
+            raise TetWildGPUError("twg_create(device=%r) failed with code %d (no sm_100-class GPU? there is no CPU fallback)" % (device, rc))
         self.h = h
         self.device = device
+
+    @property
+    def num_devices(self):
+        return int(self._L.twg_num_devices(self.h))
+
+    def set_option(self, name, value):
+        self._check(self._L.twg_set_option(self.h, name.encode(), C.c_double(value)))
+
+    def get_option(self, name):
+        v = C.c_double(0)
+        self._check(self._L.twg_get_option(self.h, name.encode(), C.byref(v)))
+        return v.value
+
+    def debug_counter(self, which=0):
+        """0: envelope queries that overflowed the traversal stack and were re-decided by the exact descent"""
+        v = C.c_uint64(0)
+        self._check(self._L.twg_debug_counter(self.h, C.c_int(which), C.byref(v)))
+        return int(v.value)
 
     def close(self):
         if getattr(self, "h", None):

@@ -160,10 +160,17 @@ __device__ __forceinline__ void gather_vertex(const double* __restrict__ V, int3
 }
 
 // calTetQuality_AMIPS (LocalOperations.cpp:862-884)
-__global__ void __launch_bounds__(256, 3) amips_quality_kernel(const double* __restrict__ V, const int4* __restrict__ tets, uint64_t nT,
-                                                            double* __restrict__ slim) {
+// A tet that names a vertex outside [0, nV) is never dereferenced: it gives MAX_ENERGY and raises the context's bad-index
+// counter (the host entry point turns that into TWG_ERR_INVALID_ARG).
+__global__ void __launch_bounds__(256, 3) amips_quality_kernel(const double* __restrict__ V, uint32_t nV, const int4* __restrict__ tets, uint64_t nT,
+                                                            double* __restrict__ slim, unsigned long long* dbg) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nT; i += (uint64_t)gridDim.x * blockDim.x) {
         const int4 t = __ldg(tets + i);
+        if ((uint32_t)t.x >= nV || (uint32_t)t.y >= nV || (uint32_t)t.z >= nV || (uint32_t)t.w >= nV) {
+            slim[i] = TWG_MAX_ENERGY;
+            atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
+            continue;
+        }
         double x[12];
         gather_vertex(V, t.x, x); gather_vertex(V, t.y, x + 3); gather_vertex(V, t.z, x + 6); gather_vertex(V, t.w, x + 9);
         double e;
@@ -207,7 +214,7 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
                                                             const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
                                                             const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
                                                             double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
-                                                            uint8_t* __restrict__ ok) {
+                                                            uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg) {
     constexpr int NRED = ENERGY_ONLY ? 1 : 10;
     __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -232,14 +239,19 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
         const bool in = k < h.cnt;
         return t_ids ? (in ? (uint32_t)__ldg(t_ids + h.b + k) : 0u) : h.b + (in ? k : 0u);
     };
-    auto stage_tet = [&](const RingHead& h, uint32_t k, uint32_t ti) -> int4 {
-        int4 t = make_int4(0, 0, 0, 0);
-        if (k < h.cnt) t = __ldg(tets + ti);
+    auto stage_tet = [&](const RingHead& h, uint32_t k, uint32_t ti) -> int4 {  // a member id outside [0, nT) reads nothing
+        int4 t = make_int4(-1, -1, -1, -1);
+        if (k < h.cnt && (uint64_t)ti < nT) t = __ldg(tets + ti);
         return t;
     };
     // one member tet: gather, evaluate, add into the lane's partial sums
     auto member = [&](int4 t, int32_t c, double* acc) {
         int32_t a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
+        // removed slots (negative first index) and out-of-range ids contribute nothing and are never dereferenced
+        if ((uint32_t)a0 >= nV || (uint32_t)a1 >= nV || (uint32_t)a2 >= nV || (uint32_t)a3 >= nV) {
+            atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
+            return;
+        }
         if (!ENERGY_ONLY) {
             // :640-651, rotate so that the first slot holding the centre vertex comes first (slot 0 when absent, like the
             // reference); getNewEnergy keeps the stored order. Two conditional register rotations: no branches, no indexing.
@@ -343,7 +355,7 @@ int launch_soa(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, 
     a.E = dE; a.J3 = dJ3; a.H9 = dH9; a.n = n;
     vec = vec && (!dE || aligned16(dE)) && (!dJ3 || aligned16(dJ3)) && (!dH9 || aligned16(dH9));
     const bool jh = (dJ3 != nullptr) || (dH9 != nullptr);
-    static const bool use_tma = [] { const char* e = getenv("TWG_AMIPS_TMA"); return e ? atoi(e) != 0 : true; }();
+    const bool use_tma = c->opt.amips_tma != 0;
     if (vec && jh && use_tma && n >= 2 * AM_THREADS) {
         // full tiles through the TMA-store kernel, the ragged rest (< 256 tets) through the generic one
         const uint64_t n_tiles = n / (2 * AM_THREADS);
@@ -388,10 +400,7 @@ unsigned grid_for(twg_ctx* c, uint64_t items, int per_block, int waves) {
 }
 
 // persistent grid of the ring kernels: 3 resident CTAs per SM (80 registers x 256 threads), every warp pipelines over its rings
-int ring_waves() {
-    static const int w = [] { const char* e = getenv("TWG_RING_WAVES"); const int v = e ? atoi(e) : 3; return v < 1 ? 1 : v; }();
-    return w;
-}
+int ring_waves(const twg_ctx* c) { return c->opt.ring_waves; }
 
 }  // namespace
 
@@ -399,60 +408,64 @@ extern "C" {
 
 int twg_amips_energy_soa_dev(twg_ctx* c, const double* const dT[12], double* dE, uint64_t n, void* stream) {
     TWG_CHECK(c, c && dT && dE, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
     return launch_soa(c, dT, dE, nullptr, nullptr, n, pick(c, stream));
 }
 
 int twg_amips_ejh_soa_dev(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, double* dH9, uint64_t n, void* stream) {
     TWG_CHECK(c, c && dT, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
     return launch_soa(c, dT, dE, dJ3, dH9, n, pick(c, stream));
 }
 
 int twg_amips_quality_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, double* dSlim, void* stream) {
-    (void)nV;
     TWG_CHECK(c, c && dV && dTets && dSlim, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nT == 0) return 0;
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, amips_quality_kernel, grid_for(c, nT, 256, 8), 256, 0, pick(c, stream), dV, (const int4*)dTets, nT, dSlim);
+    TWG_LAUNCH(c, amips_quality_kernel, grid_for(c, nT, 256, 8), 256, 0, pick(c, stream), dV, nV, (const int4*)dTets, nT, dSlim, c->dcounters);
     return 0;
 }
 
 int twg_amips_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dTids,
                            const uint64_t* dOff, const int32_t* dCenter, uint64_t nG, double* dE, double* dJ3, double* dH9,
                            uint8_t* dOk, void* stream) {
-    (void)nV; (void)nT;
     TWG_CHECK(c, c && dV && dTets && dOff && dCenter && dE && dJ3 && dH9, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nG == 0) return 0;
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves()), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
-               dCenter, (const int32_t*)nullptr, nG, dE, dJ3, dH9, dOk);
+    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
+               dCenter, (const int32_t*)nullptr, nG, dE, dJ3, dH9, dOk, nV, nT, c->dcounters);
     return 0;
 }
 
 // one-rings named by their centre vertex: members of ring g are adj_tets[adj_off[v] .. adj_off[v+1]) with v = dVids[g]
-int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, const int32_t* dTets, const int32_t* dAdjTets, const uint64_t* dAdjOff,
-                                  const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk, void* stream) {
+int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets,
+                                  const uint64_t* dAdjOff, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk,
+                                  void* stream) {
     TWG_CHECK(c, c && dV && dTets && dAdjTets && dAdjOff && dVids && dE && dJ3 && dH9, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nG == 0) return 0;
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves()), 256, 0, pick(c, stream), dV, (const int4*)dTets, dAdjTets, dAdjOff,
-               (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk);
+    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, pick(c, stream), dV, (const int4*)dTets, dAdjTets, dAdjOff,
+               (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk, nV, nT, c->dcounters);
     return 0;
 }
 
 int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dTids,
                               const uint64_t* dOff, uint64_t nG, double* dE, void* stream) {
-    (void)nV; (void)nT;
     TWG_CHECK(c, c && dV && dTets && dOff && dE, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
     if (nG == 0) return 0;
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, ring_waves()), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
-               (const int32_t*)nullptr, (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr);
+    TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
+               (const int32_t*)nullptr, (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr, nV, nT, c->dcounters);
     return 0;
 }
 
@@ -460,6 +473,16 @@ int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const i
 int twg_amips_ejh_soa(twg_ctx* c, const double* const T[12], double* E, double* J3, double* H9, uint64_t n) {
     TWG_CHECK(c, c && T, TWG_ERR_INVALID_ARG, "null argument");
     if (n == 0) return 0;
+    if (twg_is_multi(c)) {  // flat batch: contiguous index ranges, one per device
+        if (n < TWG_MULTI_MIN_TETS) return twg_forward0(c, twg_amips_ejh_soa(c->children[0], T, E, J3, H9, n));
+        const uint64_t G = c->children.size();
+        return twg_multi_run(c, [&](int k, twg_ctx* child) {
+            const uint64_t b = (n * (uint64_t)k / G) & ~1ull, e = (k + 1 == (int)G) ? n : ((n * (uint64_t)(k + 1) / G) & ~1ull);  // even starts keep 16-byte alignment
+            const double* Tk[12];
+            for (int a = 0; a < 12; ++a) Tk[a] = T[a] + b;
+            return twg_amips_ejh_soa(child, Tk, E ? E + b : nullptr, J3 ? J3 + 3 * b : nullptr, H9 ? H9 + 9 * b : nullptr, e - b);
+        });
+    }
     TWG_CUDA(c, cudaSetDevice(c->device));
     const uint64_t chunk = 1ull << 21;  // 2 Mi tets: 192 MiB in, up to 208 MiB out per slot
     const int nout = (E ? 1 : 0) + (J3 ? 3 : 0) + (H9 ? 9 : 0);
@@ -493,28 +516,57 @@ int twg_amips_energy_soa(twg_ctx* c, const double* const T[12], double* E, uint6
     return twg_amips_ejh_soa(c, T, E, nullptr, nullptr, n);
 }
 
+static int begin_checked(twg_ctx* c, cudaStream_t st);
+static int finish_checked(twg_ctx* c, cudaStream_t st);
+
 int twg_amips_quality(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, double* slim) {
     TWG_CHECK(c, c && V && tets && slim, TWG_ERR_INVALID_ARG, "null argument");
     if (nT == 0) return 0;
+    if (twg_is_multi(c)) {  // vertices replicated, tets split by index range
+        if (nT < TWG_MULTI_MIN_TETS) return twg_forward0(c, twg_amips_quality(c->children[0], V, nV, tets, nT, slim));
+        const uint64_t G = c->children.size();
+        return twg_multi_run(c, [&](int k, twg_ctx* child) {
+            const uint64_t b = nT * (uint64_t)k / G, e = nT * (uint64_t)(k + 1) / G;
+            return twg_amips_quality(child, V, nV, tets + 4 * b, e - b, slim + b);
+        });
+    }
     TWG_CUDA(c, cudaSetDevice(c->device));
     const size_t vb = ((size_t)nV * 3 * sizeof(double) + 255) & ~(size_t)255;
     const size_t tb = ((size_t)nT * 16 + 255) & ~(size_t)255;
     TWG_TRY(twg_ensure_scratch(c, 0, vb + tb + nT * sizeof(double)));
     char* base = (char*)c->dscratch[0];
     cudaStream_t st = c->streams[0];
+    TWG_TRY(begin_checked(c, st));
     TWG_CUDA(c, cudaMemcpyAsync(base, V, (size_t)nV * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     TWG_CUDA(c, cudaMemcpyAsync(base + vb, tets, (size_t)nT * 16, cudaMemcpyHostToDevice, st));
     TWG_TRY(twg_amips_quality_dev(c, (const double*)base, nV, (const int32_t*)(base + vb), nT, (double*)(base + vb + tb), st));
     TWG_CUDA(c, cudaMemcpyAsync(slim, base + vb + tb, nT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return finish_checked(c, st);
+}
+
+// The kernels never dereference an out-of-range index; they count them. The host entry points clear the counter before
+// their launch, read it with the results and report TWG_ERR_INVALID_ARG (results of the offending tets / rings are MAX_ENERGY / partial sums).
+static int begin_checked(twg_ctx* c, cudaStream_t st) {
+    TWG_CUDA(c, cudaMemsetAsync(c->dcounters + TWG_DBG_BAD_INDEX, 0, sizeof(unsigned long long), st));
+    return 0;
+}
+static int finish_checked(twg_ctx* c, cudaStream_t st) {
+    unsigned long long bad = 0;
+    TWG_CUDA(c, cudaMemcpyAsync(&bad, c->dcounters + TWG_DBG_BAD_INDEX, sizeof(bad), cudaMemcpyDeviceToHost, st));
     TWG_CUDA(c, cudaStreamSynchronize(st));
+    TWG_CHECK(c, bad == 0, TWG_ERR_INVALID_ARG, "a tet or ring references a vertex / tet out of range");
     return 0;
 }
 
 static int ring_host(twg_ctx* c, bool energy_only, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, const int32_t* t_ids,
                      const uint64_t* off, const int32_t* center, uint64_t nG, double* E, double* J3, double* H9, uint8_t* ok) {
     if (nG == 0) return 0;
+    if (twg_is_multi(c)) return twg_forward0(c, ring_host(c->children[0], energy_only, V, nV, tets, nT, t_ids, off, center, nG, E, J3, H9, ok));
     TWG_CUDA(c, cudaSetDevice(c->device));
     const uint64_t nM = off[nG];
+    TWG_CHECK(c, nM < (1ull << 32) && off[0] <= nM, TWG_ERR_INVALID_ARG, "group_off must be non-decreasing and below 2^32");
+    for (uint64_t g = 0; g < nG; ++g) TWG_CHECK(c, off[g] <= off[g + 1], TWG_ERR_INVALID_ARG, "group_off must be non-decreasing");
+    if (!t_ids) TWG_CHECK(c, nM <= nT, TWG_ERR_INVALID_ARG, "group_off runs past the tet array");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t vb = up((size_t)nV * 24), tb = up((size_t)nT * 16), ib = t_ids ? up((size_t)nM * 4) : 0, ob = up((size_t)(nG + 1) * 8),
                  cb = up((size_t)nG * 4), eb = up((size_t)nG * 8), jb = up((size_t)nG * 24), hb = up((size_t)nG * 72), kb = up((size_t)nG);
@@ -530,6 +582,7 @@ static int ring_host(twg_ctx* c, bool energy_only, const double* V, uint32_t nV,
     char* dJ = p; p += jb;
     char* dH = p; p += hb;
     char* dK = p;
+    TWG_TRY(begin_checked(c, st));
     TWG_CUDA(c, cudaMemcpyAsync(dV, V, (size_t)nV * 24, cudaMemcpyHostToDevice, st));
     TWG_CUDA(c, cudaMemcpyAsync(dT, tets, (size_t)nT * 16, cudaMemcpyHostToDevice, st));
     if (t_ids) TWG_CUDA(c, cudaMemcpyAsync(dI, t_ids, (size_t)nM * 4, cudaMemcpyHostToDevice, st));
@@ -548,8 +601,7 @@ static int ring_host(twg_ctx* c, bool energy_only, const double* V, uint32_t nV,
         TWG_CUDA(c, cudaMemcpyAsync(H9, dH, (size_t)nG * 72, cudaMemcpyDeviceToHost, st));
         if (ok) TWG_CUDA(c, cudaMemcpyAsync(ok, dK, (size_t)nG, cudaMemcpyDeviceToHost, st));
     }
-    TWG_CUDA(c, cudaStreamSynchronize(st));
-    return 0;
+    return finish_checked(c, st);
 }
 
 int twg_amips_ring_ejh(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets, uint64_t nT, const int32_t* t_ids,

@@ -4,12 +4,50 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/tetwild_gpu.h"
 #include "tw_math.cuh"
 
 #define TWG_NUM_STREAMS 3
+
+// Tuning knobs of one context. Defaults come from the environment ONCE, at twg_create (TWG_ENV_GROUP, TWG_SORT_BITS, ...:
+// the variable is "TWG_" + the upper-cased option name); twg_set_option changes them per context afterwards.
+struct twg_options {
+    int env_group = 64;        // queries per cooperative group of the envelope point kernel
+    int env_policy = 1;        // round scheduling (1) or eager refill (0)
+    int env_front = 32;        // frontier cap of a group: 16 / 32 / 64
+    int env_quorum = 16;       // parked lanes that trigger a leaf round
+    int env_top = 64;          // pair records staged in shared memory
+    int envelope_sort = 1;     // Morton-order large batches before traversal
+    int sort_bits = 24;        // Morton bits that are sorted
+    long long chunk_points = 1ll << 20;  // points per staging chunk of the host entry points
+    int ring_waves = 3;        // resident CTAs per SM of the one-ring kernels
+    int winding_minb = 3;
+    int winding_sort = 1;
+    int winding_leaf = 64;
+    int winding_device_build = 1;
+    int amips_tma = 1;
+    int nearest_mode = 1;      // 1: warp-cooperative kernel, 0: per-lane descents (round 1)
+    int trace = 0;
+};
+
+// One "lane" per CUDA stream that launches sorted / persistent kernels: its own Morton-sort scratch and its own work
+// counters, so that asynchronous calls on DIFFERENT streams never share mutable device state. Lanes 0..TWG_NUM_STREAMS-1
+// belong to the context's staging streams; a lane is created for every distinct caller stream passed to a _dev entry point
+// (at most TWG_MAX_LANES; beyond that the least recently used one is recycled after its last launch has completed).
+#define TWG_MAX_LANES 16
+struct twg_lane {
+    cudaStream_t stream = nullptr;
+    void* dsort = nullptr;
+    size_t dsort_bytes = 0;
+    unsigned long long* counters = nullptr;  // device, 8 slots
+    cudaEvent_t done = nullptr;              // recorded after the last launch that used this lane
+    uint64_t tick = 0;
+};
+
+struct twg_worker;  // host thread that drives one device of a multi-device context (multi.cu)
 
 struct twg_ctx {
     int device = 0;
@@ -23,12 +61,20 @@ struct twg_ctx {
     // device scratch, grown on demand
     void* dscratch[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
     size_t dscratch_bytes[TWG_NUM_STREAMS] = {0, 0, 0};
-    // Morton-sort scratch (qsort.cu): one per staging stream + one (TWG_SORT_LANE_EXT) for callers' own streams
-    void* dsort[TWG_NUM_STREAMS + 1] = {nullptr, nullptr, nullptr, nullptr};
-    size_t dsort_bytes[TWG_NUM_STREAMS + 1] = {0, 0, 0, 0};
+    std::vector<twg_lane> lanes;
+    uint64_t lane_tick = 0;
+    unsigned long long* dcounters = nullptr;  // device, TWG_NUM_DEBUG_COUNTERS slots (twg_debug_counter)
+    twg_options opt;
     uint64_t launches = 0;
+    // multi-device context (twg_create_multi): children[k] is an ordinary one-device context driven by workers[k]
+    std::vector<twg_ctx*> children;
+    std::vector<twg_worker*> workers;
+    twg_ctx* parent = nullptr;
     mutable char err[512] = {0};
 };
+#define TWG_NUM_DEBUG_COUNTERS 8
+#define TWG_DBG_ENV_STACK_OVERFLOW 0
+#define TWG_DBG_BAD_INDEX 1
 
 inline int twg_fail(const twg_ctx* c, int code, const char* what, const char* file, int line) {
     if (c) snprintf(c->err, sizeof(c->err), "%s (%s:%d) code=%d", what, file, line, code);
@@ -63,15 +109,21 @@ inline int twg_fail(const twg_ctx* c, int code, const char* what, const char* fi
 
 int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
 int twg_ensure_pinned(twg_ctx* c, size_t in_bytes, size_t out_bytes);
-#define TWG_SORT_LANE_EXT TWG_NUM_STREAMS
 #define TWG_SORT_MIN 4096  /* batches below this are traversed in the caller's order */
-int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box = nullptr,
+// the lane of stream `st` (created on first use); *out stays valid until the next twg_get_lane call on this context
+int twg_get_lane(twg_ctx* c, cudaStream_t st, twg_lane** out);
+// marks the lane busy until everything queued on its stream so far has completed (call after the last launch of an entry point)
+int twg_lane_mark(twg_ctx* c, twg_lane* lane);
+int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box = nullptr,
                     const double** sorted_out = nullptr);
-inline int twg_lane_of(const twg_ctx* c, cudaStream_t st) {
-    for (int k = 0; k < TWG_NUM_STREAMS; ++k)
-        if (st == c->streams[k]) return k;
-    return TWG_SORT_LANE_EXT;
-}
+inline bool twg_is_multi(const twg_ctx* c) { return c && !c->children.empty(); }
+// multi.cu: fn(k, child_k) on every device's own host thread, concurrently; first non-zero return code wins
+int twg_multi_run(twg_ctx* c, const std::function<int(int, twg_ctx*)>& fn);
+int twg_forward0(twg_ctx* c, int rc);  // rc of a call forwarded to device 0 (copies its error message)
+// batches below these sizes stay on device 0 of a multi-device context
+#define TWG_MULTI_MIN_POINTS 65536
+#define TWG_MULTI_MIN_FACES 4096
+#define TWG_MULTI_MIN_TETS 262144
 
 // ---- device helpers ----
 #if defined(__CUDACC__)

@@ -21,8 +21,7 @@ namespace {
 // Pair records [0, kTopNodes) (the top of the heap) are staged in shared memory. Measured on B200 (10 M points, 200 k
 // facets): 8 records 2.45, 64 records 2.49, 512 records (24 KiB) 2.37 G points/s -- the L1 already holds the hot top of
 // the tree, and shared memory beyond a few KiB only costs occupancy. Default: 64 records = heap levels 0..5 = 3 KiB.
-constexpr uint32_t kTopNodesMax = 512;
-static uint32_t kTopNodes = [] { const char* e = getenv("TWG_ENV_TOP"); uint32_t v = e ? (uint32_t)atoi(e) : 64u; return v > kTopNodesMax ? kTopNodesMax : (v < 4 ? 4 : v); }();
+// (option env_top, 4 .. 512)
 constexpr int kEnvThreads = 128;
 
 __device__ __forceinline__ uint32_t stage_top(const SurfaceView& S, NodePair* top, uint64_t* bar) {
@@ -67,9 +66,22 @@ struct FrontT {
 };
 
 // MINB: resident CTAs per SM the register allocation is capped for (8 -> 64 registers, 32 warps per SM); FM: frontier cap
+// The per-lane stack holds kEnvStack subtree roots. A query needs at most FM (frontier) + 7 per remaining wide step; when
+// eps is large against the facet size that can exceed the stack. A push that does not fit is NOT dropped silently: the lane
+// raises `ovf`, and if such a query would end as OUT it is decided again by the exact binary descent twd::in_envelope
+// (32-entry stack, enough for any 2^32-leaf heap), so the answer never depends on the stack size.
+constexpr int kEnvStack = 64;
+__device__ __noinline__ bool env_overflow_fallback(const SurfaceView& S, tw::V3 p, double eps2, const NodePair* top, uint32_t topN, unsigned long long* dbg) {
+    atomicAdd(dbg + TWG_DBG_ENV_STACK_OVERFLOW, 1ull);
+    uint32_t pos;
+    return twd::in_envelope(S, p, eps2, pos, top, topN);
+}
+
 template <int MINB, int FM>
 __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
-                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy, int kLeafQuorum) {
+                                                                uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy, int kLeafQuorum,
+                                                                unsigned long long* dbg) {
+    static_assert(FM <= kEnvStack, "the frontier of a group must fit the per-lane stack");
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
@@ -94,8 +106,9 @@ __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceVi
     tw::V3 p = tw::mk(0, 0, 0);
     twd::PointF q = twd::bracket(p);
     uint64_t src = 0;
-    uint32_t stack[64];
+    uint32_t stack[kEnvStack];
     int sp = 0;
+    bool ovf = false;
     for (;;) {
         const unsigned need = __ballot_sync(full, !active);
         const unsigned act = ~need;
@@ -194,6 +207,7 @@ __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceVi
                     p = tw::mk(__ldg(P + 3 * mine), __ldg(P + 3 * mine + 1), __ldg(P + 3 * mine + 2));
                     q = twd::bracket(p);
                     sp = 0;
+                    ovf = false;
                     int best = -1;
                     float bd = 0.f;
                     for (int i = 0; i < fcount; ++i) {
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceVi
             }
         } else if (active && pend_mask == 0) {
             if (sp == 0) {
-                out[src] = 1;
+                out[src] = (ovf && env_overflow_fallback(S, p, eps2, top, topN, dbg)) ? 0 : 1;
                 active = false;
             } else {
                 const uint32_t node = stack[--sp];
@@ -244,7 +258,10 @@ __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceVi
                             if (((mask >> c) & 1u) && (best < 0 || d[c] < bd)) { best = c; bd = d[c]; }
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
-                            if (((mask >> c) & 1u) && c != best && sp < 63) stack[sp++] = c0 + (uint32_t)c;
+                            if (((mask >> c) & 1u) && c != best) {
+                                if (sp < kEnvStack - 1) stack[sp++] = c0 + (uint32_t)c;  // one slot stays free for the nearest child
+                                else ovf = true;
+                            }
                         if (best >= 0) stack[sp++] = c0 + (uint32_t)best;  // nearest subtree is popped first
                     }
                 }
@@ -639,7 +656,7 @@ unsigned grid_persistent(twg_ctx* c, uint64_t items, int per_block, int ctas_per
     return (unsigned)b;
 }
 
-uint32_t top_n(const twg_surface* s) { return s->nLeafP < kTopNodes ? s->nLeafP : kTopNodes; }
+uint32_t top_n(const twg_surface* s) { const uint32_t k = (uint32_t)s->ctx->opt.env_top; return s->nLeafP < k ? s->nLeafP : k; }
 size_t top_smem(const twg_surface* s) { return (size_t)top_n(s) * sizeof(NodePair); }
 SurfaceView view_of(const twg_surface* s) { SurfaceView v = s->view(); v.topN = top_n(s); return v; }
 
@@ -650,47 +667,43 @@ extern "C" {
 int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, double eps2, uint8_t* dOut, void* stream) {
     twg_ctx* c = s ? s->ctx : nullptr;
     TWG_CHECK(c, s && dP && dOut, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device handle (twg_surface_replica)");
     TWG_CHECK(c, eps2 >= 0.0, TWG_ERR_INVALID_ARG, "eps2 must be >= 0");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
+    twg_lane* lane = nullptr;
+    TWG_TRY(twg_get_lane(c, st, &lane));
     const uint32_t* perm = nullptr;
     const double* Pq = dP;  // queries in traversal order
-    static const bool trace = getenv("TWG_TRACE") != nullptr;
-    if (trace) fprintf(stderr, "[twg] points_out_dev s=%p n=%llu st=%p lane=%d counters=%p\n", (void*)s, (unsigned long long)n, (void*)st, twg_lane_of(c, st), (void*)s->counters);
-    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm, s->sort_box, &Pq));
-    if (trace) fprintf(stderr, "[twg] sorted perm=%p Pq=%p\n", (const void*)perm, (const void*)Pq);
-    const int lane = twg_lane_of(c, st);
-    TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
-    // queries per cooperative group (tuning aid; 64 measured best on C2)
-    static const int group = [] { const char* e = getenv("TWG_ENV_GROUP"); int v = e ? atoi(e) : 64; return v < 32 ? 32 : (v > 4096 ? 4096 : v); }();
-    static const int policy = [] { const char* e = getenv("TWG_ENV_POLICY"); return e ? atoi(e) : 1; }();
-    static const int front = [] { const char* e = getenv("TWG_ENV_FRONT"); return e ? atoi(e) : kFrontMaxDefault; }();
-    static const int quorum = [] { const char* e = getenv("TWG_ENV_QUORUM"); const int v = e ? atoi(e) : kLeafQuorumDefault; return v < 1 ? 1 : (v > 32 ? 32 : v); }();
+    if (n >= TWG_SORT_MIN && c->opt.envelope_sort) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box, &Pq));
+    TWG_CUDA(c, cudaMemsetAsync(lane->counters, 0, sizeof(unsigned long long), st));
+    const int group = c->opt.env_group, policy = c->opt.env_policy, front = c->opt.env_front, quorum = c->opt.env_quorum;
     const unsigned grid = grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8);
     if (front <= 16)
-        TWG_LAUNCH(c, (env_points_kernel<8, 16>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy, quorum);
+        TWG_LAUNCH(c, (env_points_kernel<8, 16>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters);
     else if (front >= 64)
-        TWG_LAUNCH(c, (env_points_kernel<8, 64>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy, quorum);
+        TWG_LAUNCH(c, (env_points_kernel<8, 64>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters);
     else
-        TWG_LAUNCH(c, (env_points_kernel<8, 32>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, s->counters + lane, group, policy, quorum);
-    if (trace) fprintf(stderr, "[twg] launched\n");
-    return 0;
+        TWG_LAUNCH(c, (env_points_kernel<8, 32>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters);
+    return twg_lane_mark(c, lane);
 }
 
 int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFacet, double* dNearest, double* dD2, void* stream) {
     twg_ctx* c = s ? s->ctx : nullptr;
     TWG_CHECK(c, s && dP, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device handle (twg_surface_replica)");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
+    twg_lane* lane = nullptr;
+    TWG_TRY(twg_get_lane(c, st, &lane));
     const uint32_t* perm = nullptr;
-    if (n >= TWG_SORT_MIN && !s->no_sort) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dP, n, &perm, s->sort_box));
-    const int lane = twg_lane_of(c, st);
-    TWG_CUDA(c, cudaMemsetAsync(s->counters + lane, 0, sizeof(unsigned long long), st));
+    if (n >= TWG_SORT_MIN && c->opt.envelope_sort) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box));
+    TWG_CUDA(c, cudaMemsetAsync(lane->counters, 0, sizeof(unsigned long long), st));
     TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, (n + 32 * kNearRun - 1) / (32 * kNearRun), kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), dP,
-               perm, n, dFacet, dNearest, dD2, s->counters + lane);
-    return 0;
+               perm, n, dFacet, dNearest, dD2, lane->counters);
+    return twg_lane_mark(c, lane);
 }
 
 int twg_envelope_faces_out_dev(twg_surface* s, const double* dTris, uint64_t n, double sd, double eps2, uint8_t* dOut, void* stream) {
@@ -701,6 +714,7 @@ int twg_envelope_faces_out_ex_dev(twg_surface* s, const double* dTris, uint64_t 
     twg_ctx* c = s ? s->ctx : nullptr;
     TWG_CHECK(c, s && dTris && dOut, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, eps2 >= 0.0 && sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need eps2 >= 0 and finite sampling_dist > 0");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device handle (twg_surface_replica)");
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     TWG_LAUNCH(c, env_faces_kernel, grid_persistent(c, n, kEnvThreads / 32, 8), kEnvThreads, top_smem(s), pick(c, stream), view_of(s), dTris, n, sd, eps2, flags, dOut);
@@ -711,10 +725,19 @@ int twg_envelope_faces_out_ex_dev(twg_surface* s, const double* dTris, uint64_t 
 static int points_host(twg_surface* s, int what, const double* P, uint64_t n, double eps2, uint8_t* out, uint32_t* facet, double* nearest, double* d2) {
     twg_ctx* c = s->ctx;
     if (n == 0) return 0;
+    if (!s->replicas.empty()) {  // multi-device handle: contiguous index ranges, one per device (multi.cu)
+        if (n < TWG_MULTI_MIN_POINTS) return twg_forward0(c, points_host(s->replicas[0], what, P, n, eps2, out, facet, nearest, d2));
+        const uint64_t G = s->replicas.size();
+        return twg_multi_run(c, [&](int k, twg_ctx*) {
+            const uint64_t b = n * (uint64_t)k / G, e = n * (uint64_t)(k + 1) / G;
+            return points_host(s->replicas[k], what, P + 3 * b, e - b, eps2, out ? out + b : nullptr, facet ? facet + b : nullptr,
+                               nearest ? nearest + 3 * b : nullptr, d2 ? d2 + b : nullptr);
+        });
+    }
     TWG_CUDA(c, cudaSetDevice(c->device));
     // 1 Mi points (24 MiB in) per slot by default: small enough that the first copy and the last kernel, which nothing
     // overlaps, are a small part of a 10 M batch; large enough for the sort + traversal to run at full rate
-    static const uint64_t chunk_points = [] { const char* e = getenv("TWG_CHUNK_POINTS"); uint64_t v = e ? strtoull(e, nullptr, 10) : 0; return v >= 1024 ? v : (1ull << 20); }();
+    const uint64_t chunk_points = (uint64_t)c->opt.chunk_points;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     // the exact nearest search is compute-bound (6 ns per point against 1.2 ns of PCIe) and loses efficiency on small
     // launches (far queries cluster; measured 17 ns per point at 2 M, 6.4 ns at 10 M): it gets 8 Mi-point chunks
@@ -780,6 +803,14 @@ int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, do
     twg_ctx* c = s ? s->ctx : nullptr;
     TWG_CHECK(c, s && tris && out, TWG_ERR_INVALID_ARG, "null argument");
     if (n == 0) return 0;
+    if (!s->replicas.empty()) {
+        if (n < TWG_MULTI_MIN_FACES) return twg_forward0(c, twg_envelope_faces_out_ex(s->replicas[0], tris, n, sd, eps2, flags, out));
+        const uint64_t G = s->replicas.size();
+        return twg_multi_run(c, [&](int k, twg_ctx*) {
+            const uint64_t b = n * (uint64_t)k / G, e = n * (uint64_t)(k + 1) / G;
+            return twg_envelope_faces_out_ex(s->replicas[k], tris + 9 * b, e - b, sd, eps2, flags, out + b);
+        });
+    }
     TWG_CUDA(c, cudaSetDevice(c->device));
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     if (n <= 4096) {  // the faces of one local operation: pinned slabs, one copy each way (pageable copies cost ~10 us each)
@@ -814,6 +845,7 @@ int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, do
 
 int twg_sample_triangle(twg_ctx* c, const double* tri9, double sd, double* out_xyz, uint64_t cap, uint64_t* count) {
     TWG_CHECK(c, c && tri9 && count, TWG_ERR_INVALID_ARG, "null argument");
+    if (twg_is_multi(c)) return twg_forward0(c, twg_sample_triangle(c->children[0], tri9, sd, out_xyz, cap, count));
     TWG_CHECK(c, sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need finite sampling_dist > 0");
     TWG_CUDA(c, cudaSetDevice(c->device));
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };

@@ -14,7 +14,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include "common.cuh"
 
-extern "C" int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, const int32_t* dTets, const int32_t* dAdjTets,
+extern "C" int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets,
                                              const uint64_t* dAdjOff, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3,
                                              double* dH9, uint8_t* dOk, void* stream);
 
@@ -232,6 +232,8 @@ extern "C" {
 
 int twg_mesh_create(twg_ctx* c, const double* V, uint32_t nV, const int32_t* tets4, uint64_t nT, twg_mesh** out) {
     TWG_CHECK(c, c && out && (V || nV == 0) && (tets4 || nT == 0), TWG_ERR_INVALID_ARG, "null argument");
+    // the resident mesh lives on ONE device (the scheduler that mutates it is sequential): device 0 of a multi-device context
+    if (twg_is_multi(c)) return twg_forward0(c, twg_mesh_create(c->children[0], V, nV, tets4, nT, out));
     TWG_CHECK(c, nT < (1ull << 29), TWG_ERR_INVALID_ARG, "at most 2^29 tets");
     for (uint64_t t = 0; t < nT; ++t)
         if (tets4[4 * t] >= 0)  // a negative first index marks a removed slot
@@ -400,7 +402,7 @@ int twg_mesh_vertex_ring_ejh(twg_mesh* m, const int32_t* v_ids, uint64_t n, doub
         char* ho = (char*)c->pin_out[0];
         memcpy(c->pin_in[0], v_ids, n * 4);
         TWG_CUDA(c, cudaMemcpyAsync(d, c->pin_in[0], n * 4, cudaMemcpyHostToDevice, st));
-        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, (const int32_t*)m->T, m->adj_tets, m->adj_off, (const int32_t*)d, n, (double*)(d + ib),
+        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, (const int32_t*)d, n, (double*)(d + ib),
                                               (double*)(d + ib + eb), (double*)(d + ib + eb + jb), (uint8_t*)(d + ib + eb + jb + hb), st));
         TWG_CUDA(c, cudaMemcpyAsync(ho, d + ib, eb + jb + hb + (ok ? n : 0), cudaMemcpyDeviceToHost, st));
         TWG_CUDA(c, cudaStreamSynchronize(st));
@@ -426,7 +428,7 @@ int twg_mesh_vertex_ring_ejh(twg_mesh* m, const int32_t* v_ids, uint64_t n, doub
         double* dH = (double*)p; p += up256(cm * 72);
         uint8_t* dK = (uint8_t*)p;
         TWG_CUDA(c, cudaMemcpyAsync(dI, v_ids + b, k * 4, cudaMemcpyHostToDevice, st));
-        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, (const int32_t*)m->T, m->adj_tets, m->adj_off, dI, k, dE, dJ, dH, dK, st));
+        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, dI, k, dE, dJ, dH, dK, st));
         TWG_CUDA(c, cudaMemcpyAsync(E + b, dE, k * 8, cudaMemcpyDeviceToHost, st));
         TWG_CUDA(c, cudaMemcpyAsync(J3 + 3 * b, dJ, k * 24, cudaMemcpyDeviceToHost, st));
         TWG_CUDA(c, cudaMemcpyAsync(H9 + 9 * b, dH, k * 72, cudaMemcpyDeviceToHost, st));
@@ -554,7 +556,7 @@ int twg_mesh_vertex_ring_ejh_dev(twg_mesh* m, const int32_t* dVids, uint64_t n, 
     twg_ctx* c = m ? m->ctx : nullptr;
     TWG_CHECK(c, m && dVids && dE && dJ3 && dH9, TWG_ERR_INVALID_ARG, "null argument");
     TWG_TRY(twg_mesh_build_rings(m));
-    return twg_amips_vertex_ring_ejh_dev(c, m->V, (const int32_t*)m->T, m->adj_tets, m->adj_off, dVids, n, dE, dJ3, dH9, dOk, stream);
+    return twg_amips_vertex_ring_ejh_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, dVids, n, dE, dJ3, dH9, dOk, stream);
 }
 
 }  // extern "C"

@@ -67,6 +67,7 @@ extern "C" {
 
 int twg_measure_fp64_tflops(twg_ctx* c, double* tflops) {
     TWG_CHECK(c, c && tflops, TWG_ERR_INVALID_ARG, "null argument");
+    if (twg_is_multi(c)) return twg_forward0(c, twg_measure_fp64_tflops(c->children[0], tflops));
     TWG_CUDA(c, cudaSetDevice(c->device));
     TWG_TRY(twg_ensure_scratch(c, 0, 256));
     cudaStream_t st = c->streams[0];
@@ -95,6 +96,7 @@ int twg_measure_fp64_tflops(twg_ctx* c, double* tflops) {
 
 int twg_measure_fp64_tflops_distinct(twg_ctx* c, double* tflops) {
     TWG_CHECK(c, c && tflops, TWG_ERR_INVALID_ARG, "null argument");
+    if (twg_is_multi(c)) return twg_forward0(c, twg_measure_fp64_tflops_distinct(c->children[0], tflops));
     TWG_CUDA(c, cudaSetDevice(c->device));
     TWG_TRY(twg_ensure_scratch(c, 0, 4096));
     cudaStream_t st = c->streams[0];
@@ -127,6 +129,7 @@ int twg_measure_fp64_tflops_distinct(twg_ctx* c, double* tflops) {
 int twg_measure_copy_gbs(twg_ctx* c, uint64_t bytes, double* gbs) {
     TWG_CHECK(c, c && gbs, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, bytes >= (1ull << 20), TWG_ERR_INVALID_ARG, "need at least 1 MiB");
+    if (twg_is_multi(c)) return twg_forward0(c, twg_measure_copy_gbs(c->children[0], bytes, gbs));
     TWG_CUDA(c, cudaSetDevice(c->device));
     bytes &= ~(uint64_t)255;
     void *a = nullptr, *b = nullptr;

@@ -85,39 +85,37 @@ __global__ void __launch_bounds__(256) qgather_kernel(const double* __restrict__
 
 }  // namespace
 
-// perm_out[i] = index (in the caller's order) of the i-th point along the Morton curve. `lane` selects one of the
-// TWG_NUM_STREAMS + 1 sort scratch buffers of the context (one per staging stream + one for external streams).
+// perm_out[i] = index (in the caller's order) of the i-th point along the Morton curve. `lane` is the caller stream's lane
+// (twg_get_lane): its sort scratch is only ever touched by work queued on that one stream.
 // known_box (optional, host: lo xyz, hi xyz): quantise over this box (points outside are clamped to its faces)
 // instead of reducing the batch's own bounding box first -- the surface's box is what matters to both traversals.
-int twg_sort_points(twg_ctx* c, int lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box,
+int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box,
                     const double** sorted_out) {
-    TWG_CHECK(c, n < 0xffffffffull, TWG_ERR_INVALID_ARG, "at most 2^32-2 queries per call");
+    TWG_CHECK(c, n <= 0x7fffffffull, TWG_ERR_INVALID_ARG, "at most 2^31-1 queries per device call (the host entry points chunk larger batches)");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     // The keys are 30-bit Morton codes; only the top `bits` are sorted (stable): 24 bits = a 256^3 grid over the surface's
     // box = three 8-bit radix passes instead of four. Order inside a cell does not matter to the traversals (a warp's group
     // of 64 queries spans a cell or two either way).
-    static const int bits = [] { const char* e = getenv("TWG_SORT_BITS"); const int v = e ? atoi(e) : 24; return v < 8 ? 8 : (v > 30 ? 30 : v); }();
+    const int bits = c->opt.sort_bits;
     const int begin_bit = 30 - bits;
     size_t tmp_bytes = 0;
     TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                                 (int)n, begin_bit, 30, st));
-    static const bool trace = getenv("TWG_TRACE") != nullptr;
-    if (trace) fprintf(stderr, "[twg] sort lane=%d n=%llu tmp=%zu have=%zu\n", lane, (unsigned long long)n, tmp_bytes, c->dsort_bytes[lane]);
     const size_t kb = up(n * 4);
     const size_t pb = sorted_out ? up(n * 24) : 0;
     const size_t need = 256 + 4 * kb + up(tmp_bytes) + pb;
-    if (c->dsort_bytes[lane] < need) {
-        if (c->dsort[lane]) {
+    if (lane->dsort_bytes < need) {
+        if (lane->dsort) {
             TWG_CUDA(c, cudaStreamSynchronize(st));
-            TWG_CUDA(c, cudaFree(c->dsort[lane]));
-            c->dsort[lane] = nullptr;
-            c->dsort_bytes[lane] = 0;
+            TWG_CUDA(c, cudaFree(lane->dsort));
+            lane->dsort = nullptr;
+            lane->dsort_bytes = 0;
         }
         const size_t want = need + need / 8;
-        TWG_CUDA(c, cudaMalloc(&c->dsort[lane], want));
-        c->dsort_bytes[lane] = want;
+        TWG_CUDA(c, cudaMalloc(&lane->dsort, want));
+        lane->dsort_bytes = want;
     }
-    char* base = (char*)c->dsort[lane];
+    char* base = (char*)lane->dsort;
     unsigned long long* bounds = (unsigned long long*)base;
     uint32_t *keys = (uint32_t*)(base + 256), *keys2 = (uint32_t*)(base + 256 + kb), *vals = (uint32_t*)(base + 256 + 2 * kb),
              *vals2 = (uint32_t*)(base + 256 + 3 * kb);

@@ -22,12 +22,18 @@ __host__ __device__ inline double dec(unsigned long long u) {
 __global__ void init_bounds_kernel(unsigned long long* bounds) {
     if (threadIdx.x < 3) bounds[threadIdx.x] = ~0ull;      // min slots
     else if (threadIdx.x < 6) bounds[threadIdx.x] = 0ull;  // max slots
+    else if (threadIdx.x < 8) bounds[threadIdx.x] = 0ull;  // [6]: facets that name a vertex >= nV
 }
 
-__global__ void __launch_bounds__(256) bounds_kernel(const double* __restrict__ V, const uint32_t* __restrict__ F, uint32_t nF,
+// also validates the facet indices (a facet that names a vertex >= nV is counted, never dereferenced; the build then fails)
+__global__ void __launch_bounds__(256) bounds_kernel(const double* __restrict__ V, uint32_t nV, const uint32_t* __restrict__ F, uint32_t nF,
                                                      unsigned long long* bounds) {
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < nF; f += gridDim.x * blockDim.x) {
+        if (F[3 * (size_t)f] >= nV || F[3 * (size_t)f + 1] >= nV || F[3 * (size_t)f + 2] >= nV) {
+            atomicAdd(bounds + 6, 1ull);
+            continue;
+        }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const double* p = V + 3 * (size_t)F[3 * (size_t)f + k];
@@ -121,15 +127,10 @@ __global__ void __launch_bounds__(256) level_kernel(NodePair* pairs, uint32_t fi
 }
 
 int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_t nF, twg_surface** out) {
-    (void)nV;
     cudaStream_t st = c->streams[0];
     twg_surface* s = new twg_surface;
     s->ctx = c;
     s->nF = nF;
-    {
-        const char* e = getenv("TWG_ENVELOPE_SORT");
-        s->no_sort = e && e[0] == '0';
-    }
     uint32_t lp = 2;
     while (lp < nF) lp <<= 1;
     s->nLeafP = lp;
@@ -151,8 +152,7 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
     B_CUDA(cudaMalloc(&s->pairs, sizeof(NodePair) * (size_t)lp));
     B_CUDA(cudaMalloc(&s->tris, sizeof(tw::TriRec) * (size_t)nF));
     B_CUDA(cudaMalloc(&s->triV, sizeof(double) * 9 * (size_t)nF));
-    B_CUDA(cudaMalloc(&bounds, 6 * sizeof(unsigned long long)));
-    B_CUDA(cudaMalloc(&s->counters, (TWG_NUM_STREAMS + 1) * sizeof(unsigned long long)));
+    B_CUDA(cudaMalloc(&bounds, 8 * sizeof(unsigned long long)));
     B_CUDA(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)nF));
     B_CUDA(cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)nF));
     B_CUDA(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)nF));
@@ -163,11 +163,17 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
     {
         unsigned g = (nF + 255) / 256;
         if (g > (unsigned)c->sm_count * 8) g = c->sm_count * 8;
-        bounds_kernel<<<g, 256, 0, st>>>(dV, dF, nF, bounds);
+        bounds_kernel<<<g, 256, 0, st>>>(dV, nV, dF, nF, bounds);
         c->launches++;
+        // the later kernels dereference F: stop here if an index is out of range
+        unsigned long long bad = 0;
+        B_CUDA(cudaMemcpyAsync(&bad, bounds + 6, sizeof(bad), cudaMemcpyDeviceToHost, st));
+        B_CUDA(cudaStreamSynchronize(st));
+        if (bad != 0) return fail(twg_fail(c, TWG_ERR_INVALID_ARG, "facet references a vertex out of range", __FILE__, __LINE__));
         morton_kernel<<<(nF + 255) / 256, 256, 0, st>>>(dV, dF, nF, bounds, keys, vals);
         c->launches++;
     }
+    static_assert(sizeof(int) == 4, "cub takes int item counts; nF < 2^31 is checked by the callers");
     B_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)nF, 0, 63, st));
     B_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
     B_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)nF, 0, 63, st));
@@ -202,19 +208,29 @@ extern "C" {
 
 void twg_surface_destroy(twg_surface* s) {
     if (!s) return;
+    if (!s->replicas.empty()) {
+        for (twg_surface* r : s->replicas) twg_surface_destroy(r);
+        delete s;
+        return;
+    }
     if (s->ctx) cudaSetDevice(s->ctx->device);
     cudaFree(s->pairs);
     cudaFree(s->tris);
     cudaFree(s->triV);
-    cudaFree(s->counters);
     delete s;
 }
 
 uint32_t twg_surface_num_facets(const twg_surface* s) { return s ? s->nF : 0; }
+twg_surface* twg_surface_replica(twg_surface* s, int k) {
+    if (!s) return nullptr;
+    if (s->replicas.empty()) return k == 0 ? s : nullptr;
+    return (k >= 0 && k < (int)s->replicas.size()) ? s->replicas[k] : nullptr;
+}
 
 int twg_surface_create_dev(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_t nF, twg_surface** out) {
     TWG_CHECK(c, c && dV && dF && out, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, nF > 0 && nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "surface must have 1 .. 2^31-2 facets");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
     return build(c, dV, nV, dF, nF, out);
 }
@@ -222,7 +238,18 @@ int twg_surface_create_dev(twg_ctx* c, const double* dV, uint32_t nV, const uint
 int twg_surface_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_surface** out) {
     TWG_CHECK(c, c && V && F && out, TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, nF > 0 && nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "surface must have 1 .. 2^31-2 facets");
-    for (size_t k = 0; k < 3 * (size_t)nF; ++k) TWG_CHECK(c, F[k] < nV, TWG_ERR_INVALID_ARG, "facet references a vertex out of range");
+    if (twg_is_multi(c)) {  // one replica per device, each built by its own device from the caller's arrays
+        twg_surface* s = new twg_surface;
+        s->ctx = c;
+        s->nF = nF;
+        s->replicas.assign(c->children.size(), nullptr);
+        const int rc = twg_multi_run(c, [&](int k, twg_ctx* child) { return twg_surface_create(child, V, nV, F, nF, &s->replicas[k]); });
+        if (rc != 0) { twg_surface_destroy(s); return rc; }
+        s->nLeafP = s->replicas[0]->nLeafP;
+        for (int k = 0; k < 6; ++k) { s->bbox[k] = s->replicas[0]->bbox[k]; s->sort_box[k] = s->replicas[0]->sort_box[k]; }
+        *out = s;
+        return 0;
+    }
     TWG_CUDA(c, cudaSetDevice(c->device));
     double* dV = nullptr;
     uint32_t* dF = nullptr;

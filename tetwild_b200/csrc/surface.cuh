@@ -33,8 +33,7 @@ struct twg_surface {
     NodePair* pairs = nullptr;
     tw::TriRec* tris = nullptr;
     double* triV = nullptr;
-    bool no_sort = false;  // TWG_ENVELOPE_SORT=0: traverse batches in the caller's order (profiling aid)
-    unsigned long long* counters = nullptr;  // one work counter per sort lane (persistent point kernel)
+    std::vector<twg_surface*> replicas;  // handle made on a multi-device context: one replica per device (multi.cu); else empty
     double bbox[6] = {0, 0, 0, 0, 0, 0};     // lo xyz, hi xyz of the surface
     double sort_box[6] = {0, 0, 0, 0, 0, 0}; // bbox grown by 5 %: Morton quantisation box of query batches (qsort.cu)
     SurfaceView view() const { return SurfaceView{pairs, tris, triV, nF, nLeafP, 0}; }

@@ -583,6 +583,7 @@ struct twg_winding {
     uint32_t leaf = 64;  // triangles per leaf block (TWG_WINDING_LEAF)
     double sort_box[6] = {0, 0, 0, 0, 0, 0};  // surface bbox grown by 10 %: Morton quantisation box of query batches
     bool sort_queries = true;
+    std::vector<twg_winding*> replicas;  // handle made on a multi-device context: one replica per device
     WView view() const { return WView{nodes, caps, tris, nBlkP, nF}; }
 };
 
@@ -590,6 +591,11 @@ extern "C" {
 
 void twg_winding_destroy(twg_winding* w) {
     if (!w) return;
+    if (!w->replicas.empty()) {
+        for (twg_winding* r : w->replicas) twg_winding_destroy(r);
+        delete w;
+        return;
+    }
     if (w->ctx) cudaSetDevice(w->ctx->device);
     cudaFree(w->nodes);
     cudaFree(w->caps);
@@ -597,20 +603,15 @@ void twg_winding_destroy(twg_winding* w) {
     delete w;
 }
 
-int twg_winding_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out) {
-    TWG_CHECK(c, c && out && (nF == 0 || (V && F)), TWG_ERR_INVALID_ARG, "null argument");
-    for (size_t k = 0; k < 3 * (size_t)nF; ++k) TWG_CHECK(c, F[k] < nV, TWG_ERR_INVALID_ARG, "facet references a vertex out of range");
+// uploads a host-built hierarchy to one device
+static int winding_upload(twg_ctx* c, const HostTree& T, uint32_t nF, twg_winding** out) {
     TWG_CUDA(c, cudaSetDevice(c->device));
     twg_winding* w = new twg_winding;
     w->ctx = c;
     w->nF = nF;
-    const char* e1 = getenv("TWG_WINDING_LEAF");
-    if (e1 && atoi(e1) >= 2 && atoi(e1) <= 4096) w->leaf = (uint32_t)atoi(e1);
-    const char* e2 = getenv("TWG_WINDING_SORT");
-    if (e2 && e2[0] == '0') w->sort_queries = false;
+    w->leaf = (uint32_t)c->opt.winding_leaf;
+    w->sort_queries = c->opt.winding_sort != 0;
     if (nF == 0) { *out = w; return 0; }
-    HostTree T;
-    build_host_tree(V, nV, F, nF, w->leaf, T);
     for (int k = 0; k < 3; ++k) {  // root box
         const double lo = T.nodes[1].lo[k], hi = T.nodes[1].hi[k], m = 0.1 * (hi - lo);
         w->sort_box[k] = lo - m;
@@ -632,6 +633,34 @@ int twg_winding_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t*
     return 0;
 }
 
+int twg_winding_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out) {
+    TWG_CHECK(c, c && out && (nF == 0 || (V && F)), TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "at most 2^31-2 facets");
+    for (size_t k = 0; k < 3 * (size_t)nF; ++k) TWG_CHECK(c, F[k] < nV, TWG_ERR_INVALID_ARG, "facet references a vertex out of range");
+    HostTree T;
+    if (nF) build_host_tree(V, nV, F, nF, (uint32_t)c->opt.winding_leaf, T);
+    if (twg_is_multi(c)) {  // the hierarchy is built once and uploaded to every device by that device's thread
+        twg_winding* w = new twg_winding;
+        w->ctx = c;
+        w->nF = nF;
+        w->replicas.assign(c->children.size(), nullptr);
+        const int rc = twg_multi_run(c, [&](int k, twg_ctx* child) { return winding_upload(child, T, nF, &w->replicas[k]); });
+        if (rc != 0) { twg_winding_destroy(w); return rc; }
+        w->nBlkP = w->replicas[0]->nBlkP;
+        w->n_nodes = w->replicas[0]->n_nodes;
+        w->n_caps = w->replicas[0]->n_caps;
+        *out = w;
+        return 0;
+    }
+    return winding_upload(c, T, nF, out);
+}
+
+twg_winding* twg_winding_replica(twg_winding* w, int k) {
+    if (!w) return nullptr;
+    if (w->replicas.empty()) return k == 0 ? w : nullptr;
+    return (k >= 0 && k < (int)w->replicas.size()) ? w->replicas[k] : nullptr;
+}
+
 int twg_winding_stats(const twg_winding* w, uint64_t* n_nodes, uint64_t* n_caps, uint64_t* n_tris) {
     if (!w) return TWG_ERR_INVALID_ARG;
     if (n_nodes) *n_nodes = w->n_nodes;
@@ -643,7 +672,8 @@ int twg_winding_stats(const twg_winding* w, uint64_t* n_nodes, uint64_t* n_caps,
 int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* dW, uint8_t* dKeep, void* stream) {
     twg_ctx* c = w ? w->ctx : nullptr;
     TWG_CHECK(c, w && dC && (dW || dKeep), TWG_ERR_INVALID_ARG, "null argument");
-    TWG_CHECK(c, nC < 0xffffffffull, TWG_ERR_INVALID_ARG, "at most 2^32-2 queries per call");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device handle (twg_winding_replica)");
+    TWG_CHECK(c, nC <= 0x7fffffffull, TWG_ERR_INVALID_ARG, "at most 2^31-1 queries per device call (the host entry point chunks larger batches)");
     if (nC == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = pick(c, stream);
@@ -653,19 +683,28 @@ int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* 
         return 0;
     }
     const uint32_t* perm = nullptr;
-    if (w->sort_queries && nC > 32) TWG_TRY(twg_sort_points(c, twg_lane_of(c, st), st, dC, nC, &perm, w->sort_box));
+    twg_lane* lane = nullptr;
+    TWG_TRY(twg_get_lane(c, st, &lane));
+    if (w->sort_queries && nC > 32) TWG_TRY(twg_sort_points(c, lane, st, dC, nC, &perm, w->sort_box));
     const uint64_t ngroups = (nC + 31) / 32;
     unsigned grid = (unsigned)std::min<uint64_t>((ngroups + kWarps - 1) / kWarps, (uint64_t)c->sm_count * 32);
-    static const int minb = [] { const char* e = getenv("TWG_WINDING_MINB"); return e ? atoi(e) : 3; }();
-    if (minb >= 4) TWG_LAUNCH(c, winding_kernel<4>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
+    if (c->opt.winding_minb >= 4) TWG_LAUNCH(c, winding_kernel<4>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
     else TWG_LAUNCH(c, winding_kernel<3>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
-    return 0;
+    return twg_lane_mark(c, lane);
 }
 
 int twg_winding_eval(twg_winding* w, const double* C, uint64_t nC, double* W, uint8_t* keep) {
     twg_ctx* c = w ? w->ctx : nullptr;
     TWG_CHECK(c, w && C && (W || keep), TWG_ERR_INVALID_ARG, "null argument");
     if (nC == 0) return 0;
+    if (!w->replicas.empty()) {  // multi-device handle: contiguous index ranges, one per device (multi.cu)
+        if (nC < TWG_MULTI_MIN_POINTS) return twg_forward0(c, twg_winding_eval(w->replicas[0], C, nC, W, keep));
+        const uint64_t G = w->replicas.size();
+        return twg_multi_run(c, [&](int k, twg_ctx*) {
+            const uint64_t b = nC * (uint64_t)k / G, e = nC * (uint64_t)(k + 1) / G;
+            return twg_winding_eval(w->replicas[k], C + 3 * b, e - b, W ? W + b : nullptr, keep ? keep + b : nullptr);
+        });
+    }
     TWG_CUDA(c, cudaSetDevice(c->device));
     const uint64_t chunk = 1ull << 23;  // 8 Mi queries: 192 MiB in per slot
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
