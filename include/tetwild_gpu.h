@@ -70,8 +70,9 @@ const char* twg_version(void);
  * winding_leaf, winding_device_build, amips_tma, nearest_mode, trace. Values are clamped to their valid range. */
 int twg_set_option(twg_ctx* ctx, const char* name, double value);
 int twg_get_option(const twg_ctx* ctx, const char* name, double* value);
-/* diagnostics: 0 = envelope queries that overflowed the traversal stack and were re-decided by the exact binary descent */
+/* diagnostics (cumulative per context) */
 #define TWG_COUNTER_ENV_STACK_OVERFLOW 0
+#define TWG_COUNTER_WINDING_PAIRS 2 /* (query, cap point or facet) evaluations of the winding kernel so far */
 int twg_debug_counter(twg_ctx* ctx, int which, uint64_t* value);
 
 /* ---- S2: surface build (replaces MeshFacetsAABBWithEps::MeshFacetsAABBWithEps, mesh_AABB.cpp:356-379) ------------ */

@@ -56,14 +56,45 @@ def _p(a, t):
 
 
 _lib = None
+_lib_native = None
+_use_native = False
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(_LIB):
-            build()
-        L = C.CDLL(_LIB)
+def _load(path):
+    L = C.CDLL(path)
+    _restypes(L)
+    return L
+
+
+class native:
+    """`with oracle.native():` routes every oracle call through the same C sources compiled with -O3 -march=native ON THIS
+    MACHINE (the upper-bound CPU mode; the default build is the reference's Release flags, -O2, no
+    -march). Built on first use into /tmp, never shipped."""
+
+    def __enter__(self):
+        global _lib_native, _use_native
+        if _lib_native is None:
+            import hashlib
+            import tempfile
+            tag = hashlib.sha1(open("/proc/cpuinfo").read().split("flags")[1].split("\n")[0].encode()).hexdigest()[:10] if os.path.exists("/proc/cpuinfo") else "x"
+            out = os.path.join(tempfile.gettempdir(), "liboracle_native_%s.so" % tag)
+            srcs = [os.path.join(_HERE, f) for f in ("predicates.c", "amips.c", "envelope.c", "winding.c")]
+            if not os.path.exists(out) or any(os.path.getmtime(f) > os.path.getmtime(out) for f in srcs):
+                cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+                subprocess.check_call([cc, "-O3", "-march=native", "-fPIC", "-fopenmp", "-ffp-contract=off", "-std=gnu11", "-shared", "-o", out] + srcs + ["-lm"])
+            _lib_native = _load(out)
+        _use_native = True
+        return self
+
+    def __exit__(self, *a):
+        global _use_native
+        _use_native = False
+
+
+def _restypes(L):
+    if True:
+        if True:
+            pass
         L.ora_amips_energy.restype = C.c_double
         L.ora_solid_angle_w.restype = C.c_double
         L.ora_point_triangle_sqdist.restype = C.c_double
@@ -72,7 +103,16 @@ def lib():
         L.ora_sample_triangle.restype = C.c_uint64
         L.ora_wtree_stats.restype = C.c_uint64
         L.ora_surface_num_facets.restype = C.c_uint32
-        _lib = L
+
+
+def lib():
+    global _lib
+    if _use_native and _lib_native is not None:
+        return _lib_native
+    if _lib is None:
+        if not os.path.exists(_LIB):
+            build()
+        _lib = _load(_LIB)
     return _lib
 
 

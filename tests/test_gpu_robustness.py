@@ -11,30 +11,35 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("front", [32, 64])
 def test_envelope_stack_overflow_is_exact(oracle, front):
-    """eps ~ 0.25 of the diagonal on the 200 k-triangle knot: an OUT query just beyond eps admits hundreds of boxes, more
-    than the 64-entry per-lane stack (envelope.cu kEnvStack). Overflowing queries are re-decided by the exact binary
-    descent; the decisions must equal the oracle's and the fallback must actually have run."""
-    import tetwild_b200 as tw
+    """Queries near the centre of a finely tessellated sphere with eps a hair below / above their distance to it: every leaf BOX
+    is within eps (the boxes of tilted facets reach inwards) while no FACET is, so the traversal admits the whole tree and
+    the 64-entry per-lane stack (envelope.cu kEnvStack) overflows. Overflowing queries are re-decided by the exact binary
+    descent: decisions must equal brute force and the fallback must actually have run (round 1 dropped subtrees silently)."""
     c = tw.Context(0)
     c.set_option("env_front", front)
     assert c.get_option("env_front") == front
-    V, F = synth.torus_knot(1000, 100)
+    V, F = synth.uv_sphere(160, 160, noise=0.0)
     S, OS = tw.Surface(c, V, F), oracle.Surface(V, F)
     rng = np.random.default_rng(3)
-    lo, hi = V.min(0), V.max(0)
-    P = 0.5 * (lo + hi) + 1.6 * (hi - lo) * (rng.random((300000, 3)) - 0.5)
+    r = np.linalg.norm(V, axis=1).max()
+    P = rng.normal(size=(6000, 3)) * (2e-4 * r)
+    d2 = OS.sqdist_brute(P, threads=oracle.max_threads())[0]
     n0 = c.debug_counter(0)
-    total_over = 0
+    for eps2 in (0.9995 * d2.min(), float(np.median(d2)), 1.0005 * d2.max()):
+        got = S.points_out(P, eps2)
+        assert np.array_equal(got, (d2 > eps2).astype(np.uint8)), "eps2=%g: %d decisions differ" % (eps2, int((got != (d2 > eps2)).sum()))
+    assert c.debug_counter(0) - n0 > 0, "the overflow path was not exercised: make the test harder"
+    # large eps on the config-2 surface (VERDICT r01 task 6): every decision equal to the oracle's
+    V, F = synth.torus_knot(1000, 100)
+    S2, OS2 = tw.Surface(c, V, F), oracle.Surface(V, F)
+    lo, hi = V.min(0), V.max(0)
+    P = 0.5 * (lo + hi) + 1.6 * (hi - lo) * (rng.random((200000, 3)) - 0.5)
     for eps in (0.2, 0.3):
-        got = S.points_out(P, eps * eps)
-        ref = OS.points_out(P, eps * eps, threads=8)
-        assert np.array_equal(got, ref), "eps=%g: %d decisions differ" % (eps, int((got != ref).sum()))
-        assert 0.02 < got.mean() < 0.98
-        total_over = c.debug_counter(0) - n0
-    sub = rng.choice(len(P), 1500, replace=False)
-    assert np.array_equal(S.points_out(P[sub], 0.04), (OS.sqdist_brute(P[sub], threads=8)[0] > 0.04).astype(np.uint8))
-    assert total_over > 0, "the overflow path was not exercised: make the test harder"
+        got = S2.points_out(P, eps * eps)
+        ref = OS2.points_out(P, eps * eps, threads=oracle.max_threads())
+        assert np.array_equal(got, ref) and 0.02 < got.mean() < 0.98
     S.close()
+    S2.close()
     c.close()
 
 

@@ -75,6 +75,7 @@ struct twg_ctx {
 #define TWG_NUM_DEBUG_COUNTERS 8
 #define TWG_DBG_ENV_STACK_OVERFLOW 0
 #define TWG_DBG_BAD_INDEX 1
+#define TWG_DBG_WINDING_PAIRS 2
 
 inline int twg_fail(const twg_ctx* c, int code, const char* what, const char* file, int line) {
     if (c) snprintf(c->err, sizeof(c->err), "%s (%s:%d) code=%d", what, file, line, code);

@@ -152,7 +152,7 @@ __device__ __forceinline__ void eval_tris(const WView& W, uint32_t off, uint32_t
 // spill outside the tile loops), 3 -> 76 registers (24 warps). The kernel is bound by FP64 issue latency, not bandwidth.
 template <int MINB>
 __global__ void __launch_bounds__(kWThreads, MINB) winding_kernel(WView W, const double* __restrict__ Q, const uint32_t* __restrict__ perm, uint64_t n,
-                                                           double* __restrict__ Wout, uint8_t* __restrict__ keep) {
+                                                           double* __restrict__ Wout, uint8_t* __restrict__ keep, unsigned long long* dbg) {
     __shared__ __align__(128) unsigned char sbuf[kWarps * 2 * kStageBytes];
     __shared__ __align__(8) uint64_t sbar[kWarps * 2];
     __shared__ uint32_t sstack[kWarps][kStackDepth];
@@ -181,6 +181,8 @@ __global__ void __launch_bounds__(kWThreads, MINB) winding_kernel(WView W, const
         Angle acc;
         acc.init();
         int sp = 0;
+        unsigned long long pairs = 0;  // (query, cap point or facet) evaluations of this group (diagnostic: twg_debug_counter 2)
+        const unsigned nvalid = __popc(__ballot_sync(0xffffffffu, valid));
         if (lane == 0) stack[0] = 1u;
         sp = 1;
         __syncwarp();
@@ -200,10 +202,11 @@ __global__ void __launch_bounds__(kWThreads, MINB) winding_kernel(WView W, const
             const bool any = __any_sync(0xffffffffu, inside);
             if (!any) {
                 // a cap point costs about 2/3 of a leaf triangle (one norm instead of three)
-                if (2u * nd.cap_cnt < 3u * nd.tri_cnt) eval_cap(W, nd, px, py, pz, st, acc);
-                else eval_tris(W, nd.tri_off, nd.tri_cnt, px, py, pz, st, acc);
+                if (2u * nd.cap_cnt < 3u * nd.tri_cnt) { eval_cap(W, nd, px, py, pz, st, acc); pairs += (unsigned long long)nd.cap_cnt * nvalid; }
+                else { eval_tris(W, nd.tri_off, nd.tri_cnt, px, py, pz, st, acc); pairs += (unsigned long long)nd.tri_cnt * nvalid; }
             } else if (node >= W.nBlkP) {
                 eval_tris(W, nd.tri_off, nd.tri_cnt, px, py, pz, st, acc);
+                pairs += (unsigned long long)nd.tri_cnt * nvalid;
             } else {
                 if (lane == 0) { stack[sp] = 2u * node + 1u; stack[sp + 1] = 2u * node; }
                 sp += 2;
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(kWThreads, MINB) winding_kernel(WView W, const
             if (Wout) Wout[src] = w;
             if (keep) keep[src] = w > 0.5 ? 1 : 0;
         }
+        if (lane == 0) atomicAdd(dbg + TWG_DBG_WINDING_PAIRS, pairs);
         __syncwarp();
     }
 }
@@ -688,8 +692,8 @@ int twg_winding_eval_dev(twg_winding* w, const double* dC, uint64_t nC, double* 
     if (w->sort_queries && nC > 32) TWG_TRY(twg_sort_points(c, lane, st, dC, nC, &perm, w->sort_box));
     const uint64_t ngroups = (nC + 31) / 32;
     unsigned grid = (unsigned)std::min<uint64_t>((ngroups + kWarps - 1) / kWarps, (uint64_t)c->sm_count * 32);
-    if (c->opt.winding_minb >= 4) TWG_LAUNCH(c, winding_kernel<4>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
-    else TWG_LAUNCH(c, winding_kernel<3>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep);
+    if (c->opt.winding_minb >= 4) TWG_LAUNCH(c, winding_kernel<4>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep, c->dcounters);
+    else TWG_LAUNCH(c, winding_kernel<3>, grid, kWThreads, 0, st, w->view(), dC, perm, nC, dW, dKeep, c->dcounters);
     return twg_lane_mark(c, lane);
 }
 

@@ -272,6 +272,31 @@ def grid_tet_mesh(nx, ny, nz, jitter=0.25, seed=13, shuffle=True):
     return V, np.ascontiguousarray(tets)
 
 
+def cube_surface(k=41, half=0.5):
+    """Closed, outward-oriented cube of half-size `half`, every face a k x k grid of quads split in two: 12 k^2 triangles
+    (k = 41 -> 20 172, the size of the config-1 icosphere) with LARGE FLAT regions -- the surface on which a candidate face of
+    edge ~ diag/20 can lie wholly inside the envelope, so that all ~1.4 k samples of it are tested."""
+    V, F = [], []
+    lin = np.linspace(-half, half, k + 1)
+    for axis in range(3):
+        for sgn in (-1.0, 1.0):
+            base = len(V)
+            u, v = np.meshgrid(lin, lin, indexing="ij")
+            pts = np.empty((k + 1, k + 1, 3))
+            pts[..., axis] = sgn * half
+            pts[..., (axis + 1) % 3] = u
+            pts[..., (axis + 2) % 3] = v
+            V.extend(pts.reshape(-1, 3))
+            for i in range(k):
+                for j in range(k):
+                    a, b, c, d = base + i * (k + 1) + j, base + (i + 1) * (k + 1) + j, base + (i + 1) * (k + 1) + j + 1, base + i * (k + 1) + j + 1
+                    if sgn > 0:
+                        F += [(a, b, c), (a, c, d)]
+                    else:
+                        F += [(a, c, b), (a, d, c)]
+    return np.array(V, dtype=np.float64), np.array(F, dtype=np.uint32)
+
+
 def winding_queries(V, n, seed=11, scale=1.2):
     rng = np.random.default_rng(seed)
     lo, hi = V.min(0), V.max(0)
