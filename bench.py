@@ -718,7 +718,7 @@ def run_gpu(args, parts):
                 got = dD.cpu().numpy()[idx]
                 pt = dN.cpu().numpy()[idx]
                 mism = {"d2_mismatches_vs_brute_force": int((got != dref).sum()), "sample": int(len(idx)),
-                        "nearest_point_realises_d2_max_rel_err": float((np.abs(((P[idx] - pt) ** 2).sum(1) - dref) / np.maximum(dref, 1e-30)).max())}
+                        "nearest_point_realises_d2_max_err_rel_to_d2_plus_ulp": float((np.abs(((P[idx] - pt) ** 2).sum(1) - dref) / (dref + 1e-15 * np.sqrt(dref) + 1e-30)).max())}
             res.update({"h2d": n * 24, "d2h": n * 36, "extra": {"parity_vs_brute_force": mism, "surface_triangles": int(len(F)),
                                                                  "kernel": "nearest_packet_kernel" if ctx.get_option("nearest_mode") == 1 else "nearest_kernel"}})
             del dP, dF, dN, dD, S

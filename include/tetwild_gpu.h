@@ -55,7 +55,8 @@ typedef struct twg_winding twg_winding;   /* S4: winding-number hierarchy over a
 
 /* ---- context ------------------------------------------------------------------------------------------------ */
 int twg_create(twg_ctx** ctx, int device_id);
-/* one context over n_devices distinct devices (n_devices == 1 is twg_create). SURVEY.md 8(b): twg_create(ctx, device_ids, n) */
+/* one context over n_devices devices (n_devices == 1 is twg_create; an id may repeat, which puts several worker contexts on
+ * one device -- useful for testing the split on a one-GPU box). SURVEY.md 8(b): twg_create(ctx, device_ids, n) */
 int twg_create_multi(twg_ctx** ctx, const int* device_ids, int n_devices);
 int twg_num_devices(const twg_ctx* ctx);
 twg_ctx* twg_device_context(twg_ctx* ctx, int k);  /* the one-device context of device k (k = 0: ctx itself when single) */
@@ -67,7 +68,7 @@ uint64_t twg_launch_count(const twg_ctx* ctx);  /* kernels launched by this cont
 const char* twg_version(void);
 /* Tuning knobs, per context (defaults: environment variable TWG_<NAME> read once at twg_create). Names: env_group, env_policy,
  * env_front, env_quorum, env_top, envelope_sort, sort_bits, chunk_points, ring_waves, winding_minb, winding_sort,
- * winding_leaf, winding_device_build, amips_tma, nearest_mode, trace. Values are clamped to their valid range. */
+ * winding_leaf, winding_device_build, amips_tma, nearest_mode, nearest_budget, trace. Values are clamped to their valid range. */
 int twg_set_option(twg_ctx* ctx, const char* name, double value);
 int twg_get_option(const twg_ctx* ctx, const char* name, double* value);
 /* diagnostics (cumulative per context) */
@@ -110,6 +111,11 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
 /* a8 (debug / parity): the samples sampleTriangle would generate for one triangle, in the reference's order.
  * Writes at most cap points, *count = number the reference generates. */
 int twg_sample_triangle(twg_ctx* ctx, const double* tri9, double sampling_dist, double* out_xyz, uint64_t cap, uint64_t* count);
+
+/* test hook: the library's own Morton radix sort of a query batch (csrc/qsort.cu). box6 = lo xyz, hi xyz of the quantisation box
+ * (NULL: the batch's own bounding box). perm[i] = caller index of the i-th point in sorted order; keys (nullable) = the sorted
+ * 30-bit Morton keys (pairs-only form); sorted_xyz (nullable) = the points in sorted order (gathering form). */
+int twg_debug_sort_points(twg_ctx* ctx, const double* P, uint64_t n, const double* box6, uint32_t* perm, uint32_t* keys, double* sorted_xyz);
 
 /* ---- roofline denominators measured on the context's device (not on the hot path; bench.py calls them once) -------- */
 /* FP64 vector pipe: DFMA microbenchmark, 2 flops per DFMA, TFLOP/s.  Copy: 128-bit grid-stride copy, read+write GB/s. */

@@ -53,6 +53,7 @@ def harness():
     H.hh_angle_sum.restype = C.c_double
     H.hh_norm3.restype = C.c_double
     H.hh_box_d2_lb.restype = C.c_float
+    H.hh_tri_bound_lb2.restype = C.c_double
     return H
 
 

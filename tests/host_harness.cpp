@@ -83,6 +83,15 @@ double hh_tri_sqdist(const double* p, const double* v0, const double* v1, const 
     return d;
 }
 
+// oriented facet bound (tw_math.cuh::TriBound): the lower bound the nearest-facet kernels prune leaves with
+double hh_tri_bound_lb2(const double* p, const double* tri9) {
+    tw::TriRec r;
+    tw::make_trirec(tri9, tri9 + 3, tri9 + 6, 0, r);
+    tw::TriBound B;
+    tw::make_bound(tri9, (r.flags & 1u) != 0, B);
+    return tw::bound_lb2(B, tw::mk(p[0], p[1], p[2]));
+}
+
 struct Sink {
     double* out; uint64_t cap, n;
     void operator()(tw::V3 p) { if (n < cap) { out[3 * n] = p.x; out[3 * n + 1] = p.y; out[3 * n + 2] = p.z; } ++n; }

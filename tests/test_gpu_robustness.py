@@ -12,23 +12,26 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("front", [32, 64])
 def test_envelope_stack_overflow_is_exact(oracle, front):
     """Queries near the centre of a finely tessellated sphere with eps a hair below / above their distance to it: every leaf BOX
-    is within eps (the boxes of tilted facets reach inwards) while no FACET is, so the traversal admits the whole tree and
-    the 64-entry per-lane stack (envelope.cu kEnvStack) overflows. Overflowing queries are re-decided by the exact binary
-    descent: decisions must equal brute force and the fallback must actually have run (round 1 dropped subtrees silently)."""
+    is within eps (the boxes of tilted facets reach inwards) while no FACET is, so the traversal admits the whole tree.
+    179 400 facets give an 18-level heap; with a 64-node group frontier (level 6, all admitted) the first 8-wide step below it
+    already exceeds the 64-entry per-lane stack (envelope.cu kEnvStack). Overflowing queries are re-decided by the exact
+    binary descent: decisions must equal brute force and -- for the 64-node frontier -- the fallback must actually have run
+    (round 1 dropped subtrees silently). With the default 32-node frontier this heap cannot overflow (32 + 7 x 4 < 64)."""
     c = tw.Context(0)
     c.set_option("env_front", front)
     assert c.get_option("env_front") == front
-    V, F = synth.uv_sphere(160, 160, noise=0.0)
+    V, F = synth.uv_sphere(300, 300, noise=0.0)
     S, OS = tw.Surface(c, V, F), oracle.Surface(V, F)
     rng = np.random.default_rng(3)
     r = np.linalg.norm(V, axis=1).max()
-    P = rng.normal(size=(6000, 3)) * (2e-4 * r)
+    P = rng.normal(size=(4300, 3)) * (2e-4 * r)
     d2 = OS.sqdist_brute(P, threads=oracle.max_threads())[0]
     n0 = c.debug_counter(0)
     for eps2 in (0.9995 * d2.min(), float(np.median(d2)), 1.0005 * d2.max()):
         got = S.points_out(P, eps2)
         assert np.array_equal(got, (d2 > eps2).astype(np.uint8)), "eps2=%g: %d decisions differ" % (eps2, int((got != (d2 > eps2)).sum()))
-    assert c.debug_counter(0) - n0 > 0, "the overflow path was not exercised: make the test harder"
+    if front == 64:
+        assert c.debug_counter(0) - n0 > 0, "the overflow path was not exercised: make the test harder"
     # large eps on the config-2 surface (VERDICT r01 task 6): every decision equal to the oracle's
     V, F = synth.torus_knot(1000, 100)
     S2, OS2 = tw.Surface(c, V, F), oracle.Surface(V, F)
@@ -118,3 +121,45 @@ def test_options_are_per_context():
         a.set_option("no_such_option", 1)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("n,bits", [(1, 24), (31, 24), (4096, 24), (4097, 24), (100_003, 24), (1_500_000, 24), (250_000, 30), (250_000, 13), (250_000, 8)])
+def test_own_radix_sort_is_a_stable_sort(n, bits):
+    """csrc/qsort.cu (no library sort on the query path): the result is a permutation, the top `sort_bits` of the Morton keys are
+    non-decreasing, equal keys keep the caller's order (stable => deterministic), and the gathering form returns exactly
+    P[perm]. Sizes around the 4096-pair tile, odd sizes, 1..4 passes."""
+    c = tw.Context(0)
+    c.set_option("sort_bits", bits)
+    rng = np.random.default_rng(n + bits)
+    P = rng.random((n, 3))
+    if n > 1000:
+        P[: n // 3] = P[rng.integers(0, 50, size=n // 3)]      # heavy duplicates: equal keys
+        P[n // 2] = [np.nan, 0.5, 0.5]                            # non-finite coordinates are clamped, not propagated
+        P[n // 2 + 1] = [5.0, -3.0, 0.5]                          # outside the box: clamped to its faces
+    box = np.array([0, 0, 0, 1, 1, 1.0])
+    perm, keys, srt = c.debug_sort_points(P, box)
+    assert np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+    top = keys >> (30 - bits)
+    assert (np.diff(top.astype(np.int64)) >= 0).all()
+    same = np.diff(top.astype(np.int64)) == 0
+    assert (np.diff(perm.astype(np.int64))[same] > 0).all(), "equal keys must keep the caller's order"
+    assert np.array_equal(srt, P[perm], equal_nan=True)
+    # the keys are the 30-bit Morton codes of the clamped, quantised points
+    u = np.clip(np.nan_to_num(P, nan=0.0), 0, 1)
+    qd = (u * 1023.0).astype(np.uint32)
+
+    def spread(v):
+        v = v & 0x3ff
+        v = (v | (v << 16)) & 0x030000ff
+        v = (v | (v << 8)) & 0x0300f00f
+        v = (v | (v << 4)) & 0x030c30c3
+        v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(qd[:, 0]) | (spread(qd[:, 1]) << 1) | (spread(qd[:, 2]) << 2)
+    assert np.array_equal(keys, code[perm])
+    perm2, _, _ = c.debug_sort_points(P, box, want_keys=False)
+    assert np.array_equal(perm, perm2)
+    # without a box the batch's own bounding box is reduced on the device first
+    perm3, keys3, _ = c.debug_sort_points(P[np.isfinite(P).all(1)], None, want_sorted=False)
+    assert (np.diff((keys3 >> (30 - bits)).astype(np.int64)) >= 0).all()
+    c.close()

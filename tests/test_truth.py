@@ -187,3 +187,43 @@ def test_gpu_winding_vs_mpmath(ctx):
         assert np.abs(Wg - W).max() < 1e-12, (name, np.abs(Wg - W).max())
         clear = np.abs(W - 0.5) > 1e-9
         assert np.array_equal(keep[clear], (W[clear] > 0.5).astype(np.uint8)), name
+
+
+# ------------------------------------------------------------------------------------------------------- oriented facet bound
+def test_oriented_facet_bound_is_a_lower_bound(harness):
+    """tw_math.cuh::bound_lb2 (what the nearest-facet kernels prune leaves with) never exceeds the true squared distance: checked
+    against the exact-rational fixture and against 60 k random (facet, point) pairs evaluated by the exact routine, needles
+    and degenerate facets included. A bound that is too large would silently drop the nearest facet."""
+    Pq, T, d2, cond = load_trisq()
+    for i in range(len(Pq)):
+        lb = harness.hh_tri_bound_lb2(P(Pq[i]), P(np.ascontiguousarray(T[i].reshape(9))))
+        assert lb <= d2[i] * (1 + 1e-12) + 1e-300, (i, lb, d2[i])
+    rng = np.random.default_rng(8)
+    tight = []
+    for it in range(60000):
+        scale = 10.0 ** rng.uniform(-4, 1)
+        tri = rng.normal(size=(3, 3)) * scale + rng.uniform(-2, 2, size=3)
+        if it % 9 == 0:
+            tri[2] = tri[0] + (tri[1] - tri[0]) * rng.uniform(0.1, 0.9) + rng.normal(size=3) * scale * 10.0 ** rng.uniform(-9, -3)
+        if it % 13 == 0:
+            tri[2] = tri[1]
+        k = it % 4
+        if k == 0:
+            p = (tri * rng.dirichlet([1, 1, 1])[:, None]).sum(0) + rng.normal(size=3) * scale * 10.0 ** rng.uniform(-8, 0)
+        elif k == 1:
+            p = tri.mean(0) + rng.normal(size=3) * scale * 10.0 ** rng.uniform(0, 3)
+        elif k == 2:
+            p = tri[rng.integers(3)] + rng.normal(size=3) * scale * 10.0 ** rng.uniform(-10, -1)
+        else:
+            p = rng.uniform(-3, 3, size=3)
+        t9 = np.ascontiguousarray(tri.reshape(9))
+        near = np.empty(3)
+        d = harness.hh_tri_sqdist(P(p), P(t9[0:3].copy()), P(t9[3:6].copy()), P(t9[6:9].copy()), P(near))
+        lb = harness.hh_tri_bound_lb2(P(p), P(t9))
+        # the exact routine itself carries a few ulps (x condition number for needles): compare with that slack
+        far2 = ((tri - p) ** 2).sum(1).max()
+        assert lb <= d + 1e-9 * d + 1e-12 * far2, (it, lb, d)
+        if d > 0 and k == 1:
+            tight.append(lb / d)
+    # and it is worth having: for far points the bound is within a few percent of the true distance
+    assert np.median(tight) > 0.9

@@ -144,6 +144,17 @@ class Context:
     def synchronize(self):
         self._check(self._L.twg_synchronize(self.h))
 
+    def debug_sort_points(self, P, box=None, want_keys=True, want_sorted=True):
+        """the library's own Morton radix sort (csrc/qsort.cu) -> (perm, sorted keys or None, sorted points or None)"""
+        P = _f64(P)
+        n = len(P)
+        perm = np.empty(n, dtype=np.uint32)
+        keys = np.empty(n, dtype=np.uint32) if want_keys else None
+        srt = np.empty((n, 3)) if want_sorted else None
+        b = _f64(box).reshape(6) if box is not None else None
+        self._check(self._L.twg_debug_sort_points(self.h, _ptr(P), C.c_uint64(n), _ptr(b), _ptr(perm), _ptr(keys), _ptr(srt)))
+        return perm, keys, srt
+
     # ---- roofline denominators (microbenchmarks, not on the hot path) ----
     def measure_fp64_tflops(self):
         v = C.c_double(0)

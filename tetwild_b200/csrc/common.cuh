@@ -30,6 +30,7 @@ struct twg_options {
     int winding_device_build = 1;
     int amips_tma = 1;
     int nearest_mode = 1;      // 1: warp-cooperative kernel, 0: per-lane descents (round 1)
+    int nearest_budget = 96;   // node visits a packet of 32 queries may spend before its queries are finished one per warp
     int trace = 0;
 };
 
@@ -116,7 +117,7 @@ int twg_get_lane(twg_ctx* c, cudaStream_t st, twg_lane** out);
 // marks the lane busy until everything queued on its stream so far has completed (call after the last launch of an entry point)
 int twg_lane_mark(twg_ctx* c, twg_lane* lane);
 int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box = nullptr,
-                    const double** sorted_out = nullptr);
+                    const double** sorted_out = nullptr, const uint32_t** keys_out_dbg = nullptr);
 inline bool twg_is_multi(const twg_ctx* c) { return c && !c->children.empty(); }
 // multi.cu: fn(k, child_k) on every device's own host thread, concurrently; first non-zero return code wins
 int twg_multi_run(twg_ctx* c, const std::function<int(int, twg_ctx*)>& fn);

@@ -28,6 +28,7 @@ const OptDesc kOpts[] = {
     {"winding_device_build", &twg_options::winding_device_build, nullptr, 0, 1},
     {"amips_tma", &twg_options::amips_tma, nullptr, 0, 1},
     {"nearest_mode", &twg_options::nearest_mode, nullptr, 0, 1},
+    {"nearest_budget", &twg_options::nearest_budget, nullptr, 1, 1 << 30},
     {"trace", &twg_options::trace, nullptr, 0, 1},
 };
 

@@ -318,19 +318,31 @@ __global__ void __launch_bounds__(kEnvThreads, 8) nearest_kernel(SurfaceView S, 
     }
 }
 
-// Exact nearest facet for large sorted batches: PACKET traversal. A warp owns 32 consecutive Morton-sorted queries and walks
-// the tree ONCE for all of them with one shared stack (in shared memory): a node is entered iff SOME lane still needs it
-// (conservative FP32 box bound <= that lane's current best), every lane tests the same pair record (one broadcast load,
-// no divergence), the nearer child by majority goes first. Queries that are close in space need nearly the same nodes --
-// |d_i - d_j| <= |p_i - p_j| -- so the union costs little more than one traversal, all 32 lanes stay busy, and there is no
-// per-thread stack (round 1: 9.7 active lanes per instruction, 232 M local-memory accesses per 10 M points).
-// At the leaves the oriented bound (surface.cuh::TriBound, ~20 FP64 instructions) decides whether a lane runs the exact
-// ~170-instruction point-triangle routine at all: a far query's candidate leaves are those whose BOX intrudes the sphere of
-// its current best distance (a cap of radius sqrt(2 d h)), but only the handful whose PLANE patch does can be nearer.
-// Each lane starts from the facet that answered the same lane of the previous packet of its chunk (nearest_facet_with_hint,
-// mesh_AABB.h:162-176). The result is the exact minimum over all facets (same d2 bits as brute force).
+// Exact nearest facet for large sorted batches (nearest_facet, mesh_AABB.cpp:418-480): two warp-cooperative forms, no per-thread
+// stack anywhere (round 1: one descent per lane with two 32-entry stacks in local memory -- 9.7 active lanes per instruction,
+// 232 M local-memory accesses per 10 M points).
+//
+// (1) PACKET traversal -- queries near the surface. A warp owns 32 consecutive Morton-sorted queries and walks the tree ONCE for
+//     all of them with one shared stack (shared memory): a node is entered iff SOME lane still needs it (conservative FP32 box
+//     bound <= that lane's current best), every lane tests the same pair record (one broadcast load, no divergence), the
+//     nearer child by majority goes first. Queries that are close in space need nearly the same nodes (|d_i - d_j| <=
+//     |p_i - p_j|), so the union costs little more than one traversal.
+// (2) ONE QUERY PER WARP -- far queries. A far query's candidates are the ~10^2 leaves whose boxes intrude the sphere of its
+//     nearest distance (a cap of radius sqrt(2 d h)); 32 far queries of one packet lie ~0.02 apart (their density is low),
+//     their caps barely overlap, and a packet would run the exact point-triangle routine once per (leaf, interested lane).
+//     So when a packet has not finished within `budget` node visits, its queries are finished one at a time by the whole
+//     warp: the 32 lanes test 32 DIFFERENT boxes -- the eight children of four nodes popped from a shared stack -- against
+//     the SAME query, survivors are compacted back with a ballot, and at the leaf level every lane owns one facet:
+//     oriented bound, then the exact routine for the few that remain, then a warp minimum. The packet phase is not
+//     wasted: each query starts from the (already near-exact) bound it reached there.
+// At the leaves the oriented bound (surface.cuh::TriBound, ~20 FP64 instructions) decides whether the exact ~170-instruction
+// routine runs at all. Each lane starts from the facet that answered the same lane of the previous packet of its chunk
+// (nearest_facet_with_hint, mesh_AABB.h:162-176). The result is the exact minimum over all facets (same d2 bits as brute
+// force; ties between equidistant facets go to the one met first).
 constexpr int kPacketChunk = 4;   // consecutive packets per claim: three of four start from a neighbour's facet
 constexpr int kPacketStack = 40;  // one sibling per level of a heap with at most 2^32 leaves
+constexpr int kWarpStack = 1536;  // one-query-per-warp form: nodes pending on the shared stack (32 lanes x up to 8 survivors per sweep step)
+constexpr int kWarpLeaves = 512;  // ... and facets waiting for their batch
 
 struct PacketBest {
     double d2, s, t;
@@ -353,17 +365,178 @@ __device__ __forceinline__ void packet_leaf(const SurfaceView& S, uint32_t pos, 
     }
 }
 
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// form (2): the whole warp finishes ONE query. p and `b` are warp-uniform on entry (b: the bound reached so far, a real facet);
+// on exit b is the exact nearest facet, warp-uniform. Needs a heap of at least three levels (nLeafP >= 8).
+//   phase 0  greedy descent: lanes 0..7 bound the eight descendants of the current node, the nearest one is entered, down to
+//            eight facets that are tested exactly -- the bound is now within a facet size of the answer, which is what keeps the
+//            sweep small (the candidate cap grows with the square root of the slack);
+//   phase 1  sweep: every lane pops ONE node and bounds its eight descendants (one 192-byte run, twd::wide_step), the survivors
+//            of all lanes are compacted onto the shared stack with one warp scan; survivors on the facet level go to a leaf
+//            list instead;
+//   phase 2  whenever 32 facets are listed (or nothing else is left): one facet per lane, oriented bound, exact routine for
+//            the lanes that remain, warp minimum.
+struct WarpScratch {
+    uint32_t stack[kWarpStack];
+    uint32_t leaves[kWarpLeaves];
+};
+
+__device__ __forceinline__ void warp_leaf_batch(const SurfaceView& S, tw::V3 p, uint32_t pos, bool on, PacketBest& mine, double& best, float& thr) {
+    const unsigned full = 0xffffffffu;
+    bool need = false;
+    if (on && pos < S.nF) {
+        const TriBound tb = twd::load_bound(S.tb + pos);
+        need = twd::bound_lb2(tb, p) <= best * twd::kSlack;
+    }
+    if (__ballot_sync(full, need) == 0u) return;
+    bool improved = false;
+    if (need) {
+        double s_, t_; tw::V3 nd; bool deg;
+        const double d2 = twd::facet_d2(S, pos, p, s_, t_, nd, deg);
+        if (d2 < mine.d2) { mine.d2 = d2; mine.s = s_; mine.t = t_; mine.pos = pos; improved = d2 < best; }
+    }
+    if (__ballot_sync(full, improved)) {
+        best = warp_min(mine.d2);
+        thr = __double2float_ru(best * twd::kSlack);
+    }
+}
+
+__device__ __noinline__ void warp_query_nearest(const SurfaceView& S, tw::V3 p, PacketBest& b, WarpScratch* ws, const NodePair* top, uint32_t topN, int lane) {
+    const unsigned full = 0xffffffffu;
+    const twd::PointF q = twd::bracket(p);
+    const uint32_t leaf0 = S.nLeafP;
+    const int L = 31 - __clz(leaf0);
+    const uint32_t first = 1u << (L % 3);
+    uint32_t* stack = ws->stack;
+    uint32_t* leaves = ws->leaves;
+    // lane-local candidate (the incumbent lives in lane 0), warp-uniform pruning bound
+    PacketBest mine;
+    mine.d2 = (lane == 0) ? b.d2 : DBL_MAX; mine.s = b.s; mine.t = b.t; mine.pos = b.pos;
+    double best = b.d2;
+    float thr = (best < 1e37) ? __double2float_ru(best * twd::kSlack) : __int_as_float(0x7f7fffff);
+    // ---- phase 0: greedy descent
+    {
+        uint32_t node = 0;  // 0: the (virtual) parent of the `first` root-level nodes
+        for (;;) {
+            const uint32_t c0 = node ? 8u * node : first;
+            const uint32_t nchild = node ? 8u : first;
+            if (c0 >= leaf0) {  // eight facets: exact tests, no bound needed
+                warp_leaf_batch(S, p, c0 + (uint32_t)lane - leaf0, (uint32_t)lane < nchild, mine, best, thr);
+                break;
+            }
+            unsigned long long keyv = ~0ull;
+            if ((uint32_t)lane < nchild) {
+                const uint32_t child = c0 + (uint32_t)lane;
+                const float* rec = reinterpret_cast<const float*>(S.pairs + (child >> 1)) + 6 * (child & 1u);
+                const float2 u = __ldg(reinterpret_cast<const float2*>(rec));
+                const float2 v = __ldg(reinterpret_cast<const float2*>(rec) + 1);
+                const float2 w = __ldg(reinterpret_cast<const float2*>(rec) + 2);
+                const float d = twd::box_d2_lb(q, u.x, u.y, v.x, v.y, w.x, w.y);  // >= 0, +inf for padding: bit pattern is order preserving
+                keyv = ((unsigned long long)__float_as_uint(d) << 32) | child;
+            }
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(full, keyv, o);
+                keyv = other < keyv ? other : keyv;
+            }
+            keyv = __shfl_sync(full, keyv, 0);
+            node = (uint32_t)(keyv & 0xffffffffu);
+        }
+    }
+    // ---- phase 1 + 2: sweep from the root level with the tight bound
+    __syncwarp();
+    if ((uint32_t)lane < first) stack[lane] = first + (uint32_t)lane;
+    int sp = (int)first, lc = 0;
+    __syncwarp();
+    while (sp > 0 || lc > 0) {
+        if (sp > 0) {
+            int take = sp < 32 ? sp : 32;
+            const int room = (kWarpStack - sp) / 7;  // every popped node frees one slot and may push eight
+            if (take > room) take = room > 0 ? room : 1;
+            const bool on = lane < take;
+            const uint32_t node = on ? stack[sp - take + lane] : 0u;
+            sp -= take;
+            __syncwarp();
+            uint32_t mask = 0;
+            const uint32_t c0 = 8u * node;
+            if (on) {
+                float d[8];
+                mask = twd::wide_step(S, q, thr, node, top, topN, d);
+            }
+            const bool leaf_level = c0 >= leaf0;
+            // one warp scan for both destinations: low half = children pushed back, high half = facets listed
+            const uint32_t mine_cnt = on ? (leaf_level ? ((uint32_t)__popc(mask) << 16) : (uint32_t)__popc(mask)) : 0u;
+            uint32_t incl = mine_cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(full, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t tot = __shfl_sync(full, incl, 31);
+            const uint32_t excl = incl - mine_cnt;
+            if (sp + (int)(tot & 0xffffu) > kWarpStack || lc + (int)(tot >> 16) > kWarpLeaves) {
+                // (cannot happen with the room / flush rules below for heaps of up to 2^31 leaves; kept as a hard stop)
+                best = -1.0;
+                break;
+            }
+            if (on && mask) {
+                uint32_t* dst = leaf_level ? leaves + lc + (excl >> 16) : stack + sp + (excl & 0xffffu);
+                const uint32_t bias = leaf_level ? leaf0 : 0u;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if ((mask >> c) & 1u) *dst++ = c0 + (uint32_t)c - bias;
+            }
+            sp += (int)(tot & 0xffffu);
+            lc += (int)(tot >> 16);
+            __syncwarp();
+        }
+        // facets: a full batch at a time while the sweep goes on, everything once the stack is empty or the list is nearly full
+        while (lc >= 32 || (lc > 0 && (sp == 0 || lc > kWarpLeaves - 256))) {
+            const int take = lc < 32 ? lc : 32;
+            const bool on = lane < take;
+            const uint32_t pos = on ? leaves[lc - take + lane] : 0u;
+            lc -= take;
+            __syncwarp();
+            warp_leaf_batch(S, p, pos, on, mine, best, thr);
+        }
+    }
+    if (best < 0.0) {  // hard stop above: finish with the exact per-lane search (lane 0), never with a partial answer
+        twd::Nearest nb;
+        nb.d2 = mine.d2; nb.s = mine.s; nb.t = mine.t; nb.pos = mine.pos; nb.deg = false; nb.pt_deg = p;
+        if (lane == 0) {
+            nb.d2 = b.d2; nb.s = b.s; nb.t = b.t; nb.pos = b.pos;
+            twd::nearest_facet(S, p, nb, top, topN);
+            mine.d2 = nb.d2; mine.s = nb.s; mine.t = nb.t; mine.pos = nb.pos;
+        } else {
+            mine.d2 = DBL_MAX;
+        }
+        best = __shfl_sync(full, mine.d2, 0);
+    }
+    // the winner: smallest d2, lowest lane among equals (deterministic)
+    const unsigned win = __ballot_sync(full, mine.d2 == best);
+    const int src = __ffs(win) - 1;
+    b.d2 = best;
+    b.s = __shfl_sync(full, mine.s, src);
+    b.t = __shfl_sync(full, mine.t, src);
+    b.pos = __shfl_sync(full, mine.pos, src);
+}
+
 __global__ void __launch_bounds__(kEnvThreads, 6) nearest_packet_kernel(SurfaceView S, const double* __restrict__ Ps /*sorted*/, const uint32_t* __restrict__ perm,
                                                                     uint64_t n, uint32_t* __restrict__ facet, double* __restrict__ nearest,
-                                                                    double* __restrict__ d2out, unsigned long long* counter) {
+                                                                    double* __restrict__ d2out, unsigned long long* counter, int budget) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t stacks[kEnvThreads / 32][kPacketStack];
+    __shared__ WarpScratch scratch[kEnvThreads / 32];
     const uint32_t topN = stage_top(S, top, &bar);
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t* stack = stacks[wib];
+    uint32_t* stack = scratch[wib].stack;
     const uint32_t leaf0 = S.nLeafP;
     const uint64_t npackets = (n + 31) / 32;
     for (;;) {
@@ -387,9 +560,11 @@ __global__ void __launch_bounds__(kEnvThreads, 6) nearest_packet_kernel(SurfaceV
                 b.d2 = twd::facet_d2(S, hint, p, b.s, b.t, nd, deg);
             }
             float thr = (b.d2 < 1e37) ? __double2float_ru(b.d2 * twd::kSlack) : __int_as_float(0x7f7fffff);  // box bounds above this cannot hold a nearer facet
-            int sp = 0;
+            int sp = 0, visits = 0;
             uint32_t node = 1;
+            bool finished = true;
             for (;;) {
+                if (++visits > budget) { finished = false; break; }
                 const NodePair np = (node < topN) ? top[node] : twd::load_pair(S.pairs + node);
                 const float dl = twd::box_d2_lb(q, np.a.x, np.a.y, np.a.z, np.a.w, np.b.x, np.b.y);
                 const float dr = twd::box_d2_lb(q, np.b.z, np.b.w, np.c.x, np.c.y, np.c.z, np.c.w);
@@ -400,12 +575,10 @@ __global__ void __launch_bounds__(kEnvThreads, 6) nearest_packet_kernel(SurfaceV
                 if (cl >= leaf0) {
                     const uint32_t pl = cl - leaf0;
                     const double before = b.d2;
-                    if (lfirst) {
-                        if (bl) packet_leaf(S, pl, wl, p, b);
-                        if (br) packet_leaf(S, pl + 1u, wr && (double)dr <= b.d2 * twd::kSlack, p, b);
-                    } else {
-                        if (br) packet_leaf(S, pl + 1u, wr, p, b);
-                        if (bl) packet_leaf(S, pl, wl && (double)dl <= b.d2 * twd::kSlack, p, b);
+#pragma unroll 1
+                    for (int k = 0; k < 2; ++k) {
+                        const bool left = (k == 0) == lfirst;
+                        if (left ? bl : br) packet_leaf(S, left ? pl : pl + 1u, (left ? wl : wr) && (double)(left ? dl : dr) <= b.d2 * twd::kSlack, p, b);
                     }
                     if (b.d2 != before) thr = __double2float_ru(b.d2 * twd::kSlack);
                 } else if (bl | br) {
@@ -422,6 +595,23 @@ __global__ void __launch_bounds__(kEnvThreads, 6) nearest_packet_kernel(SurfaceV
                 __syncwarp();
                 node = stack[--sp];
                 __syncwarp();
+            }
+            if (!finished) {
+                // form (2): the packet's queries one at a time, each by the whole warp, from the bound it has reached
+                if (b.d2 == DBL_MAX) {  // (a heap deeper than the budget) start every query from facet 0
+                    tw::V3 nd; bool deg;
+                    b.pos = 0;
+                    b.d2 = twd::facet_d2(S, 0u, p, b.s, b.t, nd, deg);
+                }
+                const unsigned vmask = __ballot_sync(full, valid);
+                for (int k = 0; k < 32; ++k) {
+                    if (!((vmask >> k) & 1u)) continue;
+                    const tw::V3 pk = tw::mk(__shfl_sync(full, p.x, k), __shfl_sync(full, p.y, k), __shfl_sync(full, p.z, k));
+                    PacketBest bk;
+                    bk.d2 = __shfl_sync(full, b.d2, k); bk.s = __shfl_sync(full, b.s, k); bk.t = __shfl_sync(full, b.t, k); bk.pos = __shfl_sync(full, b.pos, k);
+                    warp_query_nearest(S, pk, bk, &scratch[wib], top, topN, lane);
+                    if (lane == k) b = bk;
+                }
             }
             // ---- results (scattered to the caller's order)
             if (valid) {
@@ -834,10 +1024,10 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     const bool sorted = n >= TWG_SORT_MIN && c->opt.envelope_sort;
     if (sorted) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box, &Pq));
     TWG_CUDA(c, cudaMemsetAsync(lane->counters, 0, sizeof(unsigned long long), st));
-    if (sorted && c->opt.nearest_mode == 1) {  // packets of 32 neighbouring queries share one traversal
+    if (sorted && c->opt.nearest_mode == 1 && s->nLeafP >= 8) {  // packets of 32 neighbouring queries share one traversal
         const uint64_t claims = ((n + 31) / 32 + kPacketChunk - 1) / kPacketChunk;
         TWG_LAUNCH(c, nearest_packet_kernel, grid_persistent(c, claims, kEnvThreads / 32, 6), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, dFacet,
-                   dNearest, dD2, lane->counters);
+                   dNearest, dD2, lane->counters, c->opt.nearest_budget);
         return twg_lane_mark(c, lane);
     }
     TWG_LAUNCH(c, nearest_kernel, grid_persistent(c, (n + 32 * kNearRun - 1) / (32 * kNearRun), kEnvThreads / 32, 8), kEnvThreads, top_smem(s), st, view_of(s), dP,

@@ -93,9 +93,8 @@ extern "C" int twg_create_multi(twg_ctx** out, const int* device_ids, int n_devi
     if (!out) return TWG_ERR_INVALID_ARG;
     *out = nullptr;
     if (!device_ids || n_devices < 1 || n_devices > 64) return TWG_ERR_INVALID_ARG;
-    for (int a = 0; a < n_devices; ++a)
-        for (int b = a + 1; b < n_devices; ++b)
-            if (device_ids[a] == device_ids[b]) return TWG_ERR_INVALID_ARG;
+    // ids may repeat: several worker contexts on one device (own streams, own replicas) -- how the index split is tested on a
+    // one-GPU box; a production caller names each device once
     if (n_devices == 1) return twg_create(out, device_ids[0]);
     twg_ctx* c = new twg_ctx;
     c->device = device_ids[0];

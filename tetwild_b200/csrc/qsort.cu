@@ -1,15 +1,29 @@
-// qsort.cu -- Morton ordering of a query batch on the device (shared by the envelope and winding kernels).
+// qsort.cu -- Morton ordering of a query batch on the device (shared by the envelope, nearest-facet and winding kernels).
 //
-// Both traversals are one-query-per-lane; a warp only runs at full SIMT width when its 32 queries take the same path
-// through the hierarchy and touch the same cache lines, so every large batch is first ordered along a 30-bit Morton
-// curve over its own bounding box: bbox reduction -> key kernel -> cub::DeviceRadixSort (keys + original indices).
-// The kernels then read P[perm[i]] and scatter their 1-byte / 8-byte results to the caller's positions.
-// The reference gets the same effect for free: its samples come out of sampleTriangle in spatial order and it passes
-// the previous facet as a hint (LocalOperations.cpp:1078-1086).
-#include <cub/device/device_radix_sort.cuh>
+// The traversals run at full SIMT width only when the 32 queries of a warp (the 64 of a group) walk one neighbourhood of the
+// hierarchy, so every large batch is ordered along a Morton curve over the surface's bounding box first. The reference gets
+// the same effect for free: its samples come out of sampleTriangle in spatial order and it passes the previous facet as a
+// hint (LocalOperations.cpp:1078-1086).
+//
+// Own radix sort (no library on the query path): a STABLE least-significant-digit sort of (key, original index) pairs on the
+// top `sort_bits` of a 30-bit Morton key, 8 bits per pass, written for this one job:
+//   keys_hist   one read of the points: Morton key of every point + the per-tile histogram of the first digit
+//   tile_hist   per-tile histogram of the next digit (passes 2..)
+//   row_scan    exclusive scan of every digit's counts over the tiles (one CTA per digit) + the digit totals
+//   scatter     per tile of 4096 pairs: warp-synchronous stable ranking (__match_any_sync groups lanes with equal digits; the
+//               group's first lane advances the warp's counter of that digit), the tile is staged in shared memory in digit
+//               order and written out in runs, so the global stores of one digit are contiguous. The pairs of the first pass
+//               carry an implicit index (no iota array); the LAST pass gathers the points themselves -- the kernels then
+//               read their queries as one coalesced stream and only scatter 1 B / 8 B results back through `perm`.
+// Deterministic: equal keys keep the caller's order, so a batch is traversed in the same order on every run.
 #include "common.cuh"
 
 namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 pairs per CTA
+constexpr int kSortWarps = kSortThreads / 32;
 
 __device__ __forceinline__ unsigned long long enc(double d) {  // order-preserving double -> u64
     unsigned long long b = (unsigned long long)__double_as_longlong(d);
@@ -55,32 +69,194 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
 struct Box6 {
     double v[6];  // lo xyz, hi xyz
 };
-__global__ void __launch_bounds__(256) qkeys_kernel(const double* __restrict__ Q, uint64_t n, const unsigned long long* __restrict__ bounds, Box6 known,
-                                                    uint32_t* keys, uint32_t* vals) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t code = 0;
+struct Digit {
+    int shift;
+    uint32_t mask;
+    __device__ __forceinline__ uint32_t of(uint32_t key) const { return (key >> shift) & mask; }
+};
+
+// element e of the tile owned by (warp w, round r, lane l): e = w * 512 + r * 32 + l -- increasing with (w, r, l), which is the
+// order the stable ranking below counts in
+__device__ __forceinline__ uint32_t tile_elem(int w, int r, int l) { return (uint32_t)(w * (kSortItems * 32) + r * 32 + l); }
+
+// Morton keys of the points + histogram of the first digit of every tile: hist[d * ntiles + tile]
+__global__ void __launch_bounds__(kSortThreads) qs_keys_hist_kernel(const double* __restrict__ Q, uint64_t n, const unsigned long long* __restrict__ bounds, Box6 known,
+                                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint32_t ntiles, Digit dg) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    double lo[3], inv[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const double lo = bounds ? dec(bounds[c]) : known.v[c], hi = bounds ? dec(bounds[3 + c]) : known.v[3 + c];
-        const double ext = hi - lo;
-        const double x = __ldg(Q + 3 * i + c);
-        double u = (ext > 0.0 && isfinite(x)) ? (x - lo) / ext : 0.0;
-        u = fmin(fmax(u, 0.0), 1.0);
-        code |= spread10((uint32_t)(u * 1023.0)) << c;
+        const double l = bounds ? dec(bounds[c]) : known.v[c], hgh = bounds ? dec(bounds[3 + c]) : known.v[3 + c];
+        const double ext = hgh - l;
+        lo[c] = l;
+        inv[c] = ext > 0.0 ? 1.0 / ext : 0.0;
     }
-    keys[i] = code;
-    vals[i] = (uint32_t)i;
+    const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll 4
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint64_t i = base + tile_elem(w, r, l);
+        if (i < n) {
+            uint32_t code = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double x = __ldg(Q + 3 * i + c);
+                double u = isfinite(x) ? (x - lo[c]) * inv[c] : 0.0;
+                u = fmin(fmax(u, 0.0), 1.0);
+                code |= spread10((uint32_t)(u * 1023.0)) << c;
+            }
+            keys[i] = code;
+            atomicAdd(&h[dg.of(code)], 1u);
+        }
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// Pd[i] = P[perm[i]]: the traversal kernels then read their queries as a coalesced stream (one memory round trip per
-// refill instead of the dependent perm -> point pair), only the 1-byte / 8-byte results are scattered back.
-__global__ void __launch_bounds__(256) qgather_kernel(const double* __restrict__ P, const uint32_t* __restrict__ perm, uint64_t n, double* __restrict__ Pd) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t s = (uint64_t)__ldg(perm + i);
-    const double x = __ldg(P + 3 * s), y = __ldg(P + 3 * s + 1), z = __ldg(P + 3 * s + 2);
-    Pd[3 * i] = x; Pd[3 * i + 1] = y; Pd[3 * i + 2] = z;
+__global__ void __launch_bounds__(kSortThreads) qs_tile_hist_kernel(const uint32_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ hist, uint32_t ntiles, Digit dg) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+#pragma unroll 4
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint64_t i = base + (uint64_t)r * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[dg.of(__ldg(keys + i))], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// CTA d: exclusive scan of row d of hist over the tiles (in place), total[d] = the row's sum
+__global__ void __launch_bounds__(256) qs_row_scan_kernel(uint32_t* __restrict__ hist, uint32_t ntiles, uint32_t* __restrict__ total) {
+    __shared__ uint32_t wsum[8];
+    __shared__ uint32_t carry_s;
+    uint32_t* row = hist + (size_t)blockIdx.x * ntiles;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t b = 0; b < ntiles; b += 256) {
+        const uint32_t i = b + threadIdx.x;
+        const uint32_t v = i < ntiles ? row[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int k = 0; k < w; ++k) woff += wsum[k];
+        const uint32_t carry = carry_s;
+        if (i < ntiles) row[i] = carry + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry_s = carry + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) total[blockIdx.x] = carry_s;
+}
+
+// One pass over one tile: stable ranks by digit, staging in digit order, contiguous runs out.
+//   FIRST: the pairs' indices are implicit (position in the batch); LAST with Pin: write the POINTS in sorted order + perm
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads) qs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n,
+                                                              const uint32_t* __restrict__ hist /*scanned rows*/, const uint32_t* __restrict__ total, uint32_t ntiles,
+                                                              Digit dg, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                              const double* __restrict__ Pin, double* __restrict__ Pout) {
+    __shared__ uint32_t cnt[kSortWarps][256];   // per-warp digit counters -> per-warp bases
+    __shared__ uint32_t dstart[256];            // first staged slot of every digit in this tile
+    __shared__ uint32_t gbase[256];             // global position of the tile's first element of every digit
+    __shared__ uint32_t skey[kSortTile], sval[kSortTile];
+    __shared__ uint32_t wtot[kSortWarps], wtot2[kSortWarps];
+    const unsigned full = 0xffffffffu;
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    const unsigned lt = (1u << l) - 1u;
+    const uint64_t base = (uint64_t)blockIdx.x * kSortTile;
+    const uint32_t tile_n = (uint32_t)((n - base < (uint64_t)kSortTile) ? (n - base) : (uint64_t)kSortTile);
+#pragma unroll
+    for (int k = 0; k < kSortWarps; ++k) cnt[k][threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const uint32_t e = tile_elem(w, r, l);
+        const bool valid = e < tile_n;
+        key[r] = valid ? __ldg(keys_in + base + e) : 0xffffffffu;
+        val[r] = FIRST ? (uint32_t)(base + e) : (valid ? __ldg(vals_in + base + e) : 0u);
+    }
+    // ---- stable rank inside the warp's 512 elements: round after round, lanes with equal digits form a group; the first lane of the
+    // group reads and advances the warp's counter of that digit, the others add their position in the group
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const bool valid = tile_elem(w, r, l) < tile_n;
+        const uint32_t d = dg.of(key[r]);
+        const unsigned m = __match_any_sync(full, valid ? d : (256u + (uint32_t)l));
+        const int leader = __ffs(m) - 1;
+        uint32_t b = 0;
+        if (valid && l == leader) {
+            b = cnt[w][d];
+            cnt[w][d] = b + (uint32_t)__popc(m);
+        }
+        b = __shfl_sync(full, b, leader);
+        rank[r] = b + (uint32_t)__popc(m & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+    // ---- thread d: bases of digit d over the warps, the tile's count, and (block scans) the digit's first staged slot and the
+    // number of elements with a smaller digit in the whole batch
+    {
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < kSortWarps; ++k) {
+            const uint32_t c = cnt[k][d];
+            cnt[k][d] = run;
+            run += c;
+        }
+        const uint32_t tv = __ldg(total + d);
+        uint32_t incl = run, ti = tv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(full, incl, o);
+            const uint32_t t2 = __shfl_up_sync(full, ti, o);
+            if (l >= o) { incl += t; ti += t2; }
+        }
+        if (l == 31) { wtot[w] = incl; wtot2[w] = ti; }
+        __syncthreads();
+        uint32_t woff = 0, wo2 = 0;
+        for (int k = 0; k < w; ++k) { woff += wtot[k]; wo2 += wtot2[k]; }
+        dstart[d] = woff + incl - run;
+        // global: digits below d (all tiles) + digit d in the tiles before this one
+        gbase[d] = (wo2 + ti - tv) + __ldg(hist + (size_t)d * ntiles + blockIdx.x);
+    }
+    __syncthreads();
+    // ---- stage the tile in digit order
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        if (tile_elem(w, r, l) < tile_n) {
+            const uint32_t d = dg.of(key[r]);
+            const uint32_t slot = dstart[d] + cnt[w][d] + rank[r];
+            skey[slot] = key[r];
+            sval[slot] = val[r];
+        }
+    }
+    __syncthreads();
+    // ---- write runs: staged slot i of digit d goes to gbase[d] + (i - dstart[d])
+    for (uint32_t i = threadIdx.x; i < tile_n; i += kSortThreads) {
+        const uint32_t k = skey[i], v = sval[i];
+        const uint32_t d = dg.of(k);
+        const uint32_t dst = gbase[d] + (i - dstart[d]);
+        if (Pout) {
+            const double x = __ldg(Pin + 3 * (size_t)v), y = __ldg(Pin + 3 * (size_t)v + 1), z = __ldg(Pin + 3 * (size_t)v + 2);
+            Pout[3 * (size_t)dst] = x; Pout[3 * (size_t)dst + 1] = y; Pout[3 * (size_t)dst + 2] = z;
+        } else if (keys_out) {
+            keys_out[dst] = k;
+        }
+        vals_out[dst] = v;
+    }
 }
 
 }  // namespace
@@ -89,21 +265,21 @@ __global__ void __launch_bounds__(256) qgather_kernel(const double* __restrict__
 // (twg_get_lane): its sort scratch is only ever touched by work queued on that one stream.
 // known_box (optional, host: lo xyz, hi xyz): quantise over this box (points outside are clamped to its faces)
 // instead of reducing the batch's own bounding box first -- the surface's box is what matters to both traversals.
+// sorted_out (optional): the points themselves in sorted order (gathered by the last pass).
 int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box,
-                    const double** sorted_out) {
+                    const double** sorted_out, const uint32_t** keys_out_dbg) {
     TWG_CHECK(c, n <= 0x7fffffffull, TWG_ERR_INVALID_ARG, "at most 2^31-1 queries per device call (the host entry points chunk larger batches)");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     // The keys are 30-bit Morton codes; only the top `bits` are sorted (stable): 24 bits = a 256^3 grid over the surface's
-    // box = three 8-bit radix passes instead of four. Order inside a cell does not matter to the traversals (a warp's group
-    // of 64 queries spans a cell or two either way).
+    // box = three 8-bit passes. Order inside a cell does not matter to the traversals (a warp's group of 64 queries spans a
+    // cell or two either way).
     const int bits = c->opt.sort_bits;
-    const int begin_bit = 30 - bits;
-    size_t tmp_bytes = 0;
-    TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                (int)n, begin_bit, 30, st));
+    const int passes = (bits + 7) / 8;
+    const uint32_t ntiles = (uint32_t)((n + kSortTile - 1) / kSortTile);
     const size_t kb = up(n * 4);
+    const size_t hb = up((size_t)256 * ntiles * 4);
     const size_t pb = sorted_out ? up(n * 24) : 0;
-    const size_t need = 256 + 4 * kb + up(tmp_bytes) + pb;
+    const size_t need = 1280 + 4 * kb + hb + pb;
     if (lane->dsort_bytes < need) {
         if (lane->dsort) {
             TWG_CUDA(c, cudaStreamSynchronize(st));
@@ -117,9 +293,11 @@ int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* d
     }
     char* base = (char*)lane->dsort;
     unsigned long long* bounds = (unsigned long long*)base;
-    uint32_t *keys = (uint32_t*)(base + 256), *keys2 = (uint32_t*)(base + 256 + kb), *vals = (uint32_t*)(base + 256 + 2 * kb),
-             *vals2 = (uint32_t*)(base + 256 + 3 * kb);
-    void* tmp = base + 256 + 4 * kb;
+    uint32_t* total = (uint32_t*)(base + 256);
+    uint32_t* kbuf[2] = {(uint32_t*)(base + 1280), (uint32_t*)(base + 1280 + kb)};
+    uint32_t* vbuf[2] = {(uint32_t*)(base + 1280 + 2 * kb), (uint32_t*)(base + 1280 + 3 * kb)};
+    uint32_t* hist = (uint32_t*)(base + 1280 + 4 * kb);
+    double* Pd = sorted_out ? (double*)(base + 1280 + 4 * kb + hb) : nullptr;
     Box6 known;
     for (int k = 0; k < 6; ++k) known.v[k] = known_box ? known_box[k] : 0.0;
     if (!known_box) {
@@ -128,14 +306,57 @@ int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* d
         if (g > (uint64_t)c->sm_count * 16) g = (uint64_t)c->sm_count * 16;
         TWG_LAUNCH(c, qbounds_kernel, (unsigned)g, 256, 0, st, dP, n, bounds);
     }
-    TWG_LAUNCH(c, qkeys_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, keys, vals);
-    TWG_CUDA(c, cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, begin_bit, 30, st));
-    c->launches += 2 + (bits + 7) / 8;  // cub: histogram + exclusive-sum + one onesweep pass per 8 key bits (library kernels)
-    *perm_out = vals2;
-    if (sorted_out) {
-        double* Pd = (double*)(base + 256 + 4 * kb + up(tmp_bytes));
-        TWG_LAUNCH(c, qgather_kernel, (unsigned)((n + 255) / 256), 256, 0, st, dP, vals2, n, Pd);
-        *sorted_out = Pd;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        Digit dg;
+        dg.shift = (30 - bits) + 8 * p;
+        const int width = (bits - 8 * p) < 8 ? (bits - 8 * p) : 8;
+        dg.mask = (1u << width) - 1u;
+        if (p == 0)
+            TWG_LAUNCH(c, qs_keys_hist_kernel, ntiles, kSortThreads, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, kbuf[0], hist, ntiles, dg);
+        else
+            TWG_LAUNCH(c, qs_tile_hist_kernel, ntiles, kSortThreads, 0, st, (const uint32_t*)kbuf[cur], n, hist, ntiles, dg);
+        TWG_LAUNCH(c, qs_row_scan_kernel, 256, 256, 0, st, hist, ntiles, total);
+        const bool last = p + 1 == passes;
+        const double* Pin = (last && Pd) ? dP : nullptr;
+        double* Pout = (last && Pd) ? Pd : nullptr;
+        if (p == 0)
+            TWG_LAUNCH(c, (qs_scatter_kernel<true>), ntiles, kSortThreads, 0, st, (const uint32_t*)kbuf[cur], (const uint32_t*)nullptr, n, (const uint32_t*)hist,
+                       (const uint32_t*)total, ntiles, dg, kbuf[cur ^ 1], vbuf[cur ^ 1], Pin, Pout);
+        else
+            TWG_LAUNCH(c, (qs_scatter_kernel<false>), ntiles, kSortThreads, 0, st, (const uint32_t*)kbuf[cur], (const uint32_t*)vbuf[cur], n, (const uint32_t*)hist,
+                       (const uint32_t*)total, ntiles, dg, kbuf[cur ^ 1], vbuf[cur ^ 1], Pin, Pout);
+        cur ^= 1;
     }
+    *perm_out = vbuf[cur];
+    if (sorted_out) *sorted_out = Pd;
+    if (keys_out_dbg) *keys_out_dbg = (Pd ? nullptr : kbuf[cur]);  // the last pass does not write keys when it gathers the points
     return 0;
+}
+
+// test hook (tests/test_gpu_robustness.py): sorts n host points over `box`, returns the permutation and the sorted keys
+extern "C" int twg_debug_sort_points(twg_ctx* c, const double* P, uint64_t n, const double* box6, uint32_t* perm, uint32_t* keys, double* sorted_xyz) {
+    TWG_CHECK(c, c && P && perm && n > 0, TWG_ERR_INVALID_ARG, "null argument");
+    if (twg_is_multi(c)) return twg_forward0(c, twg_debug_sort_points(c->children[0], P, n, box6, perm, keys, sorted_xyz));
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    twg_lane* lane = nullptr;
+    TWG_TRY(twg_get_lane(c, st, &lane));
+    TWG_TRY(twg_ensure_scratch(c, 0, n * 24));
+    TWG_CUDA(c, cudaMemcpyAsync(c->dscratch[0], P, n * 24, cudaMemcpyHostToDevice, st));
+    const uint32_t *dperm = nullptr, *dkeys = nullptr;
+    const double* dsorted = nullptr;
+    if (keys) {  // keys-only form (what the winding kernel uses)
+        TWG_TRY(twg_sort_points(c, lane, st, (const double*)c->dscratch[0], n, &dperm, box6, nullptr, &dkeys));
+        TWG_CUDA(c, cudaMemcpyAsync(keys, dkeys, n * 4, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaMemcpyAsync(perm, dperm, n * 4, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+    }
+    if (sorted_xyz) {  // gathering form (envelope / nearest kernels)
+        TWG_TRY(twg_sort_points(c, lane, st, (const double*)c->dscratch[0], n, &dperm, box6, &dsorted, nullptr));
+        TWG_CUDA(c, cudaMemcpyAsync(sorted_xyz, dsorted, n * 24, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaMemcpyAsync(perm, dperm, n * 4, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+    }
+    return twg_lane_mark(c, lane);
 }

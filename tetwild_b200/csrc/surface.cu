@@ -116,38 +116,8 @@ __global__ void __launch_bounds__(128) leaf_kernel(const double* __restrict__ V,
         hi[c] = __double2float_ru(fmax(fmax(tv[c], tv[3 + c]), tv[6 + c]));
     }
     store_half(pairs, nLeafP + j, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]);
-    // ---- oriented bound (surface.cuh::TriBound): smallest enclosing circle of the facet as centre, unit normal, then R and w
-    // measured from the ROUNDED centre / normal against the exact vertices and rounded up
-    const double e0[3] = {tv[3] - tv[0], tv[4] - tv[1], tv[5] - tv[2]}, e1[3] = {tv[6] - tv[0], tv[7] - tv[1], tv[8] - tv[2]};
-    const double e2[3] = {tv[6] - tv[3], tv[7] - tv[4], tv[8] - tv[5]};
-    const double l01 = e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2], l02 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
-    const double l12 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
-    const double cr[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
-    const double cr2 = cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2];
-    double c[3];
-    if (l12 >= l01 + l02) { for (int k = 0; k < 3; ++k) c[k] = 0.5 * (tv[3 + k] + tv[6 + k]); }        // obtuse at V0
-    else if (l02 >= l01 + l12) { for (int k = 0; k < 3; ++k) c[k] = 0.5 * (tv[k] + tv[6 + k]); }       // obtuse at V1
-    else if (l01 >= l02 + l12) { for (int k = 0; k < 3; ++k) c[k] = 0.5 * (tv[k] + tv[3 + k]); }       // obtuse at V2
-    else {  // circumcentre: V0 + (|e1|^2 (e0 x e1) x e0 + |e0|^2 e1 x (e0 x e1)) / (2 |e0 x e1|^2)
-        const double a[3] = {cr[1] * e0[2] - cr[2] * e0[1], cr[2] * e0[0] - cr[0] * e0[2], cr[0] * e0[1] - cr[1] * e0[0]};
-        const double b[3] = {e1[1] * cr[2] - e1[2] * cr[1], e1[2] * cr[0] - e1[0] * cr[2], e1[0] * cr[1] - e1[1] * cr[0]};
-        for (int k = 0; k < 3; ++k) c[k] = tv[k] + (l02 * a[k] + l01 * b[k]) / (2.0 * cr2);
-    }
     TriBound B;
-    B.cx = (float)c[0]; B.cy = (float)c[1]; B.cz = (float)c[2];
-    if (!isfinite(B.cx) || !isfinite(B.cy) || !isfinite(B.cz)) { B.cx = (float)tv[0]; B.cy = (float)tv[1]; B.cz = (float)tv[2]; }
-    const double inv = (cr2 > 0.0 && !(r.flags & 1u)) ? rsqrt(cr2) : 0.0;
-    B.nx = (float)(cr[0] * inv); B.ny = (float)(cr[1] * inv); B.nz = (float)(cr[2] * inv);
-    if (!isfinite(B.nx) || !isfinite(B.ny) || !isfinite(B.nz)) { B.nx = B.ny = B.nz = 0.f; }
-    double R2 = 0.0, wmax = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double dx = tv[3 * k] - (double)B.cx, dy = tv[3 * k + 1] - (double)B.cy, dz = tv[3 * k + 2] - (double)B.cz;
-        R2 = fmax(R2, dx * dx + dy * dy + dz * dz);
-        wmax = fmax(wmax, fabs(dx * (double)B.nx + dy * (double)B.ny + dz * (double)B.nz));
-    }
-    B.R = __double2float_ru(sqrt(R2) * (1.0 + 1e-6));
-    B.w = __double2float_ru(wmax * (1.0 + 1e-6) + 1e-300);
+    tw::make_bound(tv, (r.flags & 1u) != 0, B);
     tb[j] = B;
 }
 

@@ -18,18 +18,7 @@ struct __align__(16) NodePair {
 };
 static_assert(sizeof(NodePair) == 48, "NodePair is three 128-bit words");
 
-// Oriented bound of one facet (32 B): centre c and radius R of a ball that holds the facet, a unit vector n (the facet's normal,
-// rounded to float; zero for degenerate facets) and the half-thickness w of the facet along n. For ANY unit vector u,
-// |p - x|^2 = (u.(p-x))^2 + |(p-x) - u (u.(p-x))|^2, so for every x of the facet
-//   |p - x|^2 >= max(0, |n.(p-c)| - w)^2 + max(0, sqrt(|p-c|^2 - (n.(p-c))^2) - R)^2.
-// w and R are computed (rounded up) from the STORED float n and c against the exact vertices, so the bound is rigorous for
-// the stored values. Where the box bound of a leaf only knows the facet's axis-aligned extent, this bound knows its plane:
-// the exact nearest search tests ~10x fewer facets with the full point-triangle routine (nearest_packet_kernel).
-struct __align__(16) TriBound {
-    float cx, cy, cz, R;
-    float nx, ny, nz, w;
-};
-static_assert(sizeof(TriBound) == 32, "TriBound is two 128-bit words");
+using tw::TriBound;  // oriented bound of one facet: tw_math.cuh
 
 struct SurfaceView {
     const NodePair* pairs;
@@ -104,18 +93,7 @@ __device__ __forceinline__ TriBound load_bound(const TriBound* p) {
     r.nx = b.x; r.ny = b.y; r.nz = b.z; r.w = b.w;
     return r;
 }
-// rigorous lower bound of the squared distance from p to the facet behind `b` (see TriBound); evaluated in double: the float
-// fields convert exactly, |n| is within 1.2e-7 of 1 (covered by the 5e-7 deflations), and the rounding of the double
-// operations (a few 1e-16 |p-c|^2) by the last term
-__device__ __forceinline__ double bound_lb2(const TriBound& b, tw::V3 p) {
-    const double dx = p.x - (double)b.cx, dy = p.y - (double)b.cy, dz = p.z - (double)b.cz;
-    const double pi = dx * (double)b.nx + dy * (double)b.ny + dz * (double)b.nz;
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    const double a = fmax(fabs(pi) - (double)b.w, 0.0);
-    const double lat = sqrt(fmax(r2 - pi * pi * (1.0 + 5e-7), 0.0)) - (double)b.R;
-    const double l = fmax(lat, 0.0);
-    return a * a * (1.0 - 5e-7) + l * l - 1e-14 * r2;
-}
+using tw::bound_lb2;
 
 // Conservative single-precision box test: tw_math.cuh (host/device, so that the CPU tier can check its rigor)
 using tw::PointF;

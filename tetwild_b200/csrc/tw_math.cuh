@@ -108,6 +108,68 @@ TW_HD float box_d2_lb(const PointF& q, float lx, float ly, float lz, float hx, f
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Oriented bound of one facet (32 B): centre c and radius R of a ball that holds the facet, a unit vector n (the facet's normal,
+// rounded to float; zero for degenerate facets) and the half-thickness w of the facet along n. For ANY unit vector u,
+// |p - x|^2 = (u.(p-x))^2 + |(p-x) - u (u.(p-x))|^2, so for every x of the facet
+//   |p - x|^2 >= max(0, |n.(p-c)| - w)^2 + max(0, sqrt(|p-c|^2 - (n.(p-c))^2) - R)^2.
+// w and R are computed (rounded up) from the STORED float n and c against the exact vertices, so the bound is rigorous for
+// the stored values. Where the box bound of a leaf only knows the facet's axis-aligned extent, this bound knows its plane:
+// the exact nearest search runs the full point-triangle routine on ~10x fewer facets (envelope.cu, nearest_packet_kernel).
+// Host build: the same source (tests/test_host_core.py checks the bound against the exact routine and exact rationals).
+// ------------------------------------------------------------------------------------------------------------
+struct __attribute__((aligned(16))) TriBound {
+    float cx, cy, cz, R;
+    float nx, ny, nz, w;
+};
+static_assert(sizeof(TriBound) == 32, "TriBound is two 128-bit words");
+
+TW_HD void make_bound(const double* tv /*9 doubles: V0 V1 V2*/, bool degenerate, TriBound& B) {
+    const double e0[3] = {tv[3] - tv[0], tv[4] - tv[1], tv[5] - tv[2]}, e1[3] = {tv[6] - tv[0], tv[7] - tv[1], tv[8] - tv[2]};
+    const double e2[3] = {tv[6] - tv[3], tv[7] - tv[4], tv[8] - tv[5]};
+    const double l01 = e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2], l02 = e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2];
+    const double l12 = e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2];
+    const double cr[3] = {e0[1] * e1[2] - e0[2] * e1[1], e0[2] * e1[0] - e0[0] * e1[2], e0[0] * e1[1] - e0[1] * e1[0]};
+    const double cr2 = cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2];
+    // centre of the smallest enclosing circle: midpoint of the longest edge for an obtuse facet, else the circumcentre
+    double c[3];
+    if (l12 >= l01 + l02) { for (int k = 0; k < 3; ++k) c[k] = 0.5 * (tv[3 + k] + tv[6 + k]); }
+    else if (l02 >= l01 + l12) { for (int k = 0; k < 3; ++k) c[k] = 0.5 * (tv[k] + tv[6 + k]); }
+    else if (l01 >= l02 + l12) { for (int k = 0; k < 3; ++k) c[k] = 0.5 * (tv[k] + tv[3 + k]); }
+    else {  // V0 + (|e1|^2 (e0 x e1) x e0 + |e0|^2 e1 x (e0 x e1)) / (2 |e0 x e1|^2)
+        const double a[3] = {cr[1] * e0[2] - cr[2] * e0[1], cr[2] * e0[0] - cr[0] * e0[2], cr[0] * e0[1] - cr[1] * e0[0]};
+        const double b[3] = {e1[1] * cr[2] - e1[2] * cr[1], e1[2] * cr[0] - e1[0] * cr[2], e1[0] * cr[1] - e1[1] * cr[0]};
+        for (int k = 0; k < 3; ++k) c[k] = tv[k] + (l02 * a[k] + l01 * b[k]) / (2.0 * cr2);
+    }
+    B.cx = (float)c[0]; B.cy = (float)c[1]; B.cz = (float)c[2];
+    if (!(fabs((double)B.cx) <= 3e38) || !(fabs((double)B.cy) <= 3e38) || !(fabs((double)B.cz) <= 3e38)) { B.cx = (float)tv[0]; B.cy = (float)tv[1]; B.cz = (float)tv[2]; }
+    const double inv = (cr2 > 0.0 && !degenerate) ? 1.0 / sqrt(cr2) : 0.0;
+    B.nx = (float)(cr[0] * inv); B.ny = (float)(cr[1] * inv); B.nz = (float)(cr[2] * inv);
+    if (!(fabs((double)B.nx) <= 2.0) || !(fabs((double)B.ny) <= 2.0) || !(fabs((double)B.nz) <= 2.0)) { B.nx = B.ny = B.nz = 0.f; }
+    // R and w from the ROUNDED centre / normal against the exact vertices, rounded up
+    double R2 = 0.0, wmax = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double dx = tv[3 * k] - (double)B.cx, dy = tv[3 * k + 1] - (double)B.cy, dz = tv[3 * k + 2] - (double)B.cz;
+        R2 = fmax(R2, dx * dx + dy * dy + dz * dz);
+        wmax = fmax(wmax, fabs(dx * (double)B.nx + dy * (double)B.ny + dz * (double)B.nz));
+    }
+    B.R = f_up(sqrt(R2) * (1.0 + 1e-6));
+    B.w = f_up(wmax * (1.0 + 1e-6) + 1e-300);
+}
+
+// rigorous lower bound of the squared distance from p to the facet behind `b`; evaluated in double: the float fields
+// convert exactly, |n| is within 1.2e-7 of 1 (covered by the 5e-7 deflations), and the rounding of the double operations
+// (a few 1e-16 |p-c|^2) by the last term
+TW_HD double bound_lb2(const TriBound& b, V3 p) {
+    const double dx = p.x - (double)b.cx, dy = p.y - (double)b.cy, dz = p.z - (double)b.cz;
+    const double pi = dx * (double)b.nx + dy * (double)b.ny + dz * (double)b.nz;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    const double a = fmax(fabs(pi) - (double)b.w, 0.0);
+    const double lat = sqrt(fmax(r2 - pi * pi * (1.0 + 5e-7), 0.0)) - (double)b.R;
+    const double l = fmax(lat, 0.0);
+    return a * a * (1.0 - 5e-7) + l * l - 1e-14 * r2;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Point-triangle squared distance: the 7-region minimisation of Q(s,t) = |V0 + s e0 + t e1 - p|^2 (D. Eberly).
 // This is the leaf routine of the reference tree (mesh_AABB.cpp:153-171 -> geogram point_triangle_squared_distance).
 // The query-independent terms are precomputed once per facet into a 128-byte record (TriRec) with the same
