@@ -194,6 +194,47 @@ inline void energy_ispc(Context& ctx, const double* V1_x, const double* V1_y, co
     ctx.check(twg_amips_energy_soa(ctx.handle(), T, E, (uint64_t)(count < 0 ? 0 : count)));
 }
 
+/* DelaunayTetrahedralization::getVoxelPoints (DelaunayTetrahedralization.cpp:61-106): the voxel-stuffing grid over [p_min, p_max]
+ * -- N[i] = (int)(D_i / voxel_resolution) + 1 cells per axis (:76-80), planes p_min + d (j+1) plus the two box faces (:82-88), the eight
+ * box corners left out (:95-97) -- filtered by distance to the input surface: a grid point is kept iff squared_distance(p) >=
+ * voxel_resolution^2 / 4 (:92,:99-100). The reference asks the tree once per grid point; here ONE batched nearest query.
+ * voxel_resolution is bbox_diag / 20 when the relative target edge length is below 5 (%), else the absolute edge length (:67-71).
+ * The reference forms the plane coordinates in exact rationals and converts them to double; here one fused multiply-add
+ * (a single rounding of the same exact value). Appends to voxel_points in the reference's order (i, j, k nested). */
+inline double voxel_resolution(double relative_edge_length_percent, double absolute_edge_length, double bbox_diag) {
+    return relative_edge_length_percent < 5.0 ? bbox_diag / 20.0 : absolute_edge_length;
+}
+inline void getVoxelPoints(const double p_min[3], const double p_max[3], const MeshFacetsAABBWithEps& geo_face_tree, double voxel_resolution,
+                           std::vector<std::array<double, 3> >& voxel_points) {
+    std::vector<double> ds[3];
+    for (int i = 0; i < 3; ++i) {
+        const double D = p_max[i] - p_min[i];
+        const int N = (int)(D / voxel_resolution) + 1;
+        const double d = D / N;
+        ds[i].push_back(p_min[i]);
+        for (int j = 0; j < N - 1; ++j) ds[i].push_back(std::fma(d, (double)(j + 1), p_min[i]));
+        ds[i].push_back(p_max[i]);
+    }
+    std::vector<double> P;
+    P.reserve(3 * ds[0].size() * ds[1].size() * ds[2].size());
+    for (size_t i = 0; i < ds[0].size(); ++i)
+        for (size_t j = 0; j < ds[1].size(); ++j)
+            for (size_t k = 0; k < ds[2].size(); ++k) {
+                if ((i == 0 || i == ds[0].size() - 1) && (j == 0 || j == ds[1].size() - 1) && (k == 0 || k == ds[2].size() - 1)) continue;
+                P.push_back(ds[0][i]); P.push_back(ds[1][j]); P.push_back(ds[2][k]);
+            }
+    const uint64_t n = P.size() / 3;
+    if (n == 0) return;
+    std::vector<double> d2(n);
+    geo_face_tree.squared_distances(P.data(), n, d2.data());
+    const double min_dis = voxel_resolution * voxel_resolution / 4;
+    for (uint64_t q = 0; q < n; ++q) {
+        if (d2[q] < min_dis) continue;
+        std::array<double, 3> pt = {{P[3 * q], P[3 * q + 1], P[3 * q + 2]}};
+        voxel_points.push_back(pt);
+    }
+}
+
 /* State::State (State.cpp:24-41): the kernel parameters derived from the user's eps_rel, --stage and the bbox diagonal, with
  * the reference's own expressions (eps_2 is compared bit for bit, so the threshold must be the same double):
  *   sampling_dist = eps_input / stage;  eps = eps_input - sampling_dist / sqrt(3) * (stage + 1 - sub_stage);  eps_2 = eps * eps

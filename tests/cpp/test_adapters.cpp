@@ -114,6 +114,41 @@ int main() {
     ora_surface* osf = ora_surface_create(geo_sf_mesh.vertices.xyz.data(), geo_sf_mesh.vertices.nb(), geo_sf_mesh.facets.idx.data(), geo_sf_mesh.facets.nb(), 1);
     ora_surface* ob = ora_surface_create(geo_b_mesh.vertices.xyz.data(), geo_b_mesh.vertices.nb(), geo_b_mesh.facets.idx.data(), geo_b_mesh.facets.nb(), 1);
 
+    // ---------------- voxel stuffing: DelaunayTetrahedralization::getVoxelPoints (DelaunayTetrahedralization.cpp:61-106) ----------------
+    {
+        const double p_min[3] = {-0.55, -0.6, -0.52}, p_max[3] = {0.55, 0.58, 0.61};
+        const double diag = std::sqrt(1.1 * 1.1 + 1.18 * 1.18 + 1.13 * 1.13);
+        const double vr = twg::voxel_resolution(/*relative edge length, %*/ 2.0, /*absolute*/ 0.02 * diag, diag);
+        EXPECT(vr == diag / 20.0, "voxel resolution rule");
+        std::vector<std::array<double, 3> > vox;
+        twg::getVoxelPoints(p_min, p_max, geo_sf_tree, vr, vox);
+        // the reference's loop, one tree query per grid point, against the oracle
+        std::vector<double> ds[3];
+        for (int i = 0; i < 3; ++i) {
+            const double D = p_max[i] - p_min[i];
+            const int Ni = (int)(D / vr) + 1;
+            const double d = D / Ni;
+            ds[i].push_back(p_min[i]);
+            for (int j = 0; j < Ni - 1; ++j) ds[i].push_back(std::fma(d, (double)(j + 1), p_min[i]));
+            ds[i].push_back(p_max[i]);
+        }
+        size_t k_out = 0, grid = 0, mism = 0;
+        for (size_t i = 0; i < ds[0].size(); ++i)
+            for (size_t j = 0; j < ds[1].size(); ++j)
+                for (size_t k = 0; k < ds[2].size(); ++k) {
+                    if ((i == 0 || i == ds[0].size() - 1) && (j == 0 || j == ds[1].size() - 1) && (k == 0 || k == ds[2].size() - 1)) continue;
+                    ++grid;
+                    const double q[3] = {ds[0][i], ds[1][j], ds[2][k]};
+                    double od = 0;
+                    ora_point_sqdist(osf, q, 1, &od, 1);
+                    if (od < vr * vr / 4) continue;
+                    if (k_out >= vox.size() || vox[k_out][0] != q[0] || vox[k_out][1] != q[1] || vox[k_out][2] != q[2]) ++mism;
+                    ++k_out;
+                }
+        EXPECT(mism == 0 && k_out == vox.size(), "getVoxelPoints: %zu kept vs %zu by the reference loop, %zu differ", vox.size(), k_out, mism);
+        EXPECT(k_out > grid / 2 && k_out < grid, "degenerate voxel test: %zu of %zu grid points kept", k_out, grid);
+    }
+
     // isPointOutEnvelop / isPointOutBoundaryEnvelop, one point at a time like EdgeCollapser.cpp:311-329
     int n_out = 0;
     for (int i = 0; i < 300; ++i) {

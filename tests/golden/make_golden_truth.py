@@ -10,6 +10,8 @@ Independent evidence for the arithmetic that cannot be pinned bit for bit to a t
   trisq_exact_golden.json   2 000 point-triangle squared distances in EXACT rational arithmetic (fractions.Fraction on the
                             double inputs), rounded to the nearest double: bounds geogram's
                             point_triangle_squared_distance restatement (oracle/envelope.c, csrc/tw_math.cuh)
+  dihedral_mp_golden.json   min / max dihedral angles of 600 tets from the mathematical definition at 40 digits: bounds the
+                            restatement of CGAL's plane / projection constructions behind calTetQuality_AD (oracle/amips.c)
   winding_mp_golden.json    generalized winding numbers of ~2 000 (surface, query) pairs as 40-digit mpmath sums of
                             Van Oosterom-Strackee solid angles: bounds the libigl restatement (oracle/winding.c) and the
                             device's complex-product accumulation (csrc/winding.cu)
@@ -220,8 +222,46 @@ def winding_truth():
                "cases": cases}, open(os.path.join(HERE, "winding_mp_golden.json"), "w"))
 
 
+# ------------------------------------------------------------------------------------------------- mpmath dihedral angles
+def dihedral_truth():
+    """min / max dihedral angle of 600 tets from the mathematical definition -- the angle between the two faces that meet in an
+    edge, acos(-N_a . N_b) with N_i the unit normal of the face opposite vertex i pointing towards vertex i -- at 40 digits.
+    Independent of the CGAL plane / projection constructions calTetQuality_AD goes through (LocalOperations.cpp:783-860)."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(12)
+    T = synth.random_tets(600, seed=33, scale_lo=1e-2, scale_hi=1e2)         # (12, n)
+    X = T.T.reshape(-1, 4, 3)
+    X[::7, 3] = X[::7, :3].mean(1) + 0.05 * (X[::7, 3] - X[::7, :3].mean(1))  # some flat ones (small and large angles)
+    lo, hi = [], []
+    for x in X:
+        v = [[mp.mpf(float(c)) for c in p] for p in x]
+
+        def sub(a, b):
+            return [a[k] - b[k] for k in range(3)]
+
+        def cross(a, b):
+            return [a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]]
+
+        def dot(a, b):
+            return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+        N = []
+        for i in range(4):
+            o = [v[(i + 1) % 4], v[(i + 2) % 4], v[(i + 3) % 4]]
+            n = cross(sub(o[1], o[0]), sub(o[2], o[0]))
+            if dot(n, sub(v[i], o[0])) < 0:
+                n = [-c for c in n]
+            ln = mp.sqrt(dot(n, n))
+            N.append([c / ln for c in n])
+        ang = [mp.acos(max(mp.mpf(-1), min(mp.mpf(1), -dot(N[a], N[b])))) for a in range(4) for b in range(a + 1, 4)]
+        lo.append(float(min(ang)))
+        hi.append(float(max(ang)))
+    json.dump({"source": "mpmath, 40 digits: dihedral angle at the edge shared by the faces opposite vertices a and b = acos(-N_a . N_b)",
+               "n": len(X), "X": hx(X), "min_d_angle": hx(lo), "max_d_angle": hx(hi)}, open(os.path.join(HERE, "dihedral_mp_golden.json"), "w"))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["amips", "trisq", "winding"]
+    what = sys.argv[1:] or ["amips", "trisq", "winding", "dihedral"]
     O.build()
     if "amips" in what:
         amips_truth()
@@ -229,7 +269,9 @@ if __name__ == "__main__":
         trisq_truth()
     if "winding" in what:
         winding_truth()
-    for fn in ("amips_truth_golden.json", "trisq_exact_golden.json", "winding_mp_golden.json"):
+    if "dihedral" in what:
+        dihedral_truth()
+    for fn in ("amips_truth_golden.json", "trisq_exact_golden.json", "winding_mp_golden.json", "dihedral_mp_golden.json"):
         p = os.path.join(HERE, fn)
         if os.path.exists(p):
             print(fn, os.path.getsize(p), "bytes")

@@ -51,7 +51,9 @@ def test_multi_context_matches_single_device(devs, ctx, oracle):
     Q = synth.winding_queries(Vs, 400_003, seed=3)
     W1, k1 = tw.Winding(ctx, Vs, Fs).eval(Q)
     Wm, km = tw.Winding(m, Vs, Fs).eval(Q)
-    assert np.array_equal(W1, Wm) and np.array_equal(k1, km)
+    # a warp of 32 Morton-neighbours shares one traversal, so cutting the batch differently regroups the queries and changes the
+    # order in which a query's terms are added: W agrees to rounding, the decisions exactly
+    assert np.abs(W1 - Wm).max() < 1e-12 and np.array_equal(k1, km)
     keep, retried = m.inout_filter(Vs, Fs[:, [0, 2, 1]], Q[:200_000])      # flip-and-retry through the split path
     assert retried and np.array_equal(keep, k1[:200_000])
     # flat AMIPS batch

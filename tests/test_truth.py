@@ -227,3 +227,40 @@ def test_oriented_facet_bound_is_a_lower_bound(harness):
             tight.append(lb / d)
     # and it is worth having: for far points the bound is within a few percent of the true distance
     assert np.median(tight) > 0.9
+
+
+# ------------------------------------------------------------------------------------------------------- dihedral angles
+def load_dihedral():
+    g = load_golden("dihedral_mp_golden.json")
+    n = g["n"]
+    return unhex(g["X"], (n, 4, 3)), unhex(g["min_d_angle"]), unhex(g["max_d_angle"])
+
+
+def dihedral_tol(lo, hi):
+    """acos amplifies the rounding of its argument by 1 / sin(angle): a few ulps of cos become 1e-16 / sin"""
+    return 2e-13 / np.maximum(np.minimum(np.sin(lo), np.sin(hi)), 1e-3)
+
+
+def test_dihedral_oracle_vs_mpmath(oracle):
+    """calTetQuality_AD goes through CGAL plane / projection constructions that cannot be compiled here; the restatement
+    (oracle/amips.c::tet_dihedral) is checked against the mathematical definition of the dihedral angle at 40 digits"""
+    X, lo, hi = load_dihedral()
+    V = X.reshape(-1, 3)
+    T = np.arange(len(V), dtype=np.int32).reshape(-1, 4)
+    a, b = oracle.tet_dihedral(V, T, threads=2)
+    tol = dihedral_tol(lo, hi)
+    assert (np.abs(a - lo) <= tol).all() and (np.abs(b - hi) <= tol).all(), (np.abs(a - lo).max(), np.abs(b - hi).max())
+    assert lo.min() < 0.2 and hi.max() > 2.8        # the fixture does hold flat tets
+
+
+@pytest.mark.gpu
+def test_gpu_dihedral_vs_mpmath(ctx):
+    import tetwild_b200 as tw
+    X, lo, hi = load_dihedral()
+    V = X.reshape(-1, 3)
+    T = np.arange(len(V), dtype=np.int32).reshape(-1, 4)
+    M = tw.TetMesh(ctx, V, T)
+    a, b = M.dihedral()
+    M.close()
+    tol = dihedral_tol(lo, hi)
+    assert (np.abs(a - lo) <= tol).all() and (np.abs(b - hi) <= tol).all()

@@ -345,6 +345,191 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
     }
 }
 
+// amips_ring_kernel with the VERTEX GATHER as a pipeline stage of its own (round 2). In the kernel above a ring's last dependent
+// load -- the 72 B of its members' vertices -- is the one the warp waits for (ncu r01: long_scoreboard 2.8, 0.41 of the HBM
+// peak at 94 B/tet of traffic, i.e. no wasted bytes, only latency). Here every lane hands the twelve coordinates of ITS member
+// of ring i+1 to the asynchronous copy unit (cp.async, 8 B each -- a vertex is only 8-byte aligned) before it evaluates its
+// member of ring i from shared memory: the gather is in flight during ~150 FP64 instructions and needs no registers.
+// Stages per iteration: row(i+5), CSR bounds(i+4), member ids(i+3), tet records(i+2), vertices(i+1) -> shared memory, evaluate(i).
+// Shared memory: 2 stages x 12 coordinates x 32 lanes x 8 B = 6 KiB per warp, component-major (conflict-free 64-bit reads).
+template <bool ENERGY_ONLY>
+__global__ void __launch_bounds__(256, 3) amips_ring_async_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
+                                                                  const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
+                                                                  const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
+                                                                  double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
+                                                                  uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg) {
+    constexpr int NRED = ENERGY_ONLY ? 1 : 10;
+    extern __shared__ __align__(16) double dyn[];                       // [8 warps][2 stages][12][32]
+    __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* vb = dyn + (size_t)wib * 2 * 12 * 32;
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint64_t gl = nG - 1;  // prefetches past the end re-read the last ring (valid addresses, never consumed)
+
+    auto stage_row = [&](uint64_t g) -> uint32_t {
+        const uint64_t gg = g < gl ? g : gl;
+        return vids ? (uint32_t)__ldg(vids + gg) : (uint32_t)gg;
+    };
+    auto stage_head = [&](uint64_t g, uint32_t row) -> RingHead {
+        const uint64_t gg = g < gl ? g : gl;
+        const uint64_t b = __ldg(off + row), e = __ldg(off + row + 1);
+        RingHead h;
+        h.b = (uint32_t)b; h.cnt = (uint32_t)(e - b);
+        h.c = vids ? (int32_t)row : (ENERGY_ONLY ? 0 : __ldg(center + gg));
+        return h;
+    };
+    auto stage_tid = [&](const RingHead& h, uint32_t k) -> uint32_t {
+        const bool in = k < h.cnt;
+        return t_ids ? (in ? (uint32_t)__ldg(t_ids + h.b + k) : 0u) : h.b + (in ? k : 0u);
+    };
+    auto stage_tet = [&](const RingHead& h, uint32_t k, uint32_t ti) -> int4 {
+        int4 t = make_int4(-1, -1, -1, -1);
+        if (k < h.cnt && (uint64_t)ti < nT) t = __ldg(tets + ti);
+        return t;
+    };
+    // centre to slot 0 (:640-651); getNewEnergy keeps the stored order. Returns false for a tet that must not be dereferenced.
+    auto rotate = [&](int4 t, int32_t c, int32_t* a) -> bool {
+        int32_t a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
+        if ((uint32_t)a0 >= nV || (uint32_t)a1 >= nV || (uint32_t)a2 >= nV || (uint32_t)a3 >= nV) return false;
+        if (!ENERGY_ONLY) {
+            const int start = (a0 == c) ? 0 : (a1 == c) ? 1 : (a2 == c) ? 2 : (a3 == c) ? 3 : 0;
+            const bool r1 = (start & 1) != 0, r2 = (start & 2) != 0;
+            const int32_t b0 = r1 ? a1 : a0, b1 = r1 ? a2 : a1, b2 = r1 ? a3 : a2, b3 = r1 ? a0 : a3;
+            a0 = r2 ? b2 : b0; a1 = r2 ? b3 : b1; a2 = r2 ? b0 : b2; a3 = r2 ? b1 : b3;
+        }
+        a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+        return true;
+    };
+    // stage "vertices": the lane's member of ring h -> shared-memory stage st (one commit group per ring, empty or not)
+    auto stage_verts = [&](const RingHead& h, int4 t, int st) -> bool {
+        bool okm = false;
+        if ((uint32_t)lane < h.cnt) {
+            int32_t a[4];
+            okm = rotate(t, h.c, a);
+            if (okm) {
+                double* dst = vb + (size_t)st * 12 * 32 + lane;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const double* src = V + 3 * (size_t)a[v];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) cp_async8(dst + (3 * v + k) * 32, src + k);
+                }
+            } else {
+                atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
+            }
+        }
+        cp_async_commit();
+        return okm;
+    };
+    auto accumulate = [&](const double* x, double* acc) {
+        tw::Amips r;
+        tw::amips_eval<!ENERGY_ONLY>(x, r);
+        acc[0] += r.E;
+        if (!ENERGY_ONLY) {
+            acc[1] += r.J[0]; acc[2] += r.J[1]; acc[3] += r.J[2];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[4 + k] += r.H[k];
+        }
+    };
+
+    // ---- prologue
+    uint64_t g = warp;
+    RingHead h_cur = stage_head(g, stage_row(g));
+    int4 tet_cur = stage_tet(h_cur, lane, stage_tid(h_cur, lane));
+    RingHead h_n1 = stage_head(g + nwarps, stage_row(g + nwarps));
+    int4 tet_n1 = stage_tet(h_n1, lane, stage_tid(h_n1, lane));
+    RingHead h_n2 = stage_head(g + 2 * nwarps, stage_row(g + 2 * nwarps));
+    uint32_t ti_n2 = stage_tid(h_n2, lane);
+    RingHead h_n3 = stage_head(g + 3 * nwarps, stage_row(g + 3 * nwarps));
+    uint32_t row_n4 = stage_row(g + 4 * nwarps);
+    int st = 0;
+    bool ok_cur = stage_verts(h_cur, tet_cur, st);   // ring g -> stage 0
+
+    for (; g < nG; g += nwarps) {
+        // ---- issue the loads of the later rings first
+        const uint32_t row_n5 = stage_row(g + 5 * nwarps);
+        const RingHead h_n4 = stage_head(g + 4 * nwarps, row_n4);
+        const uint32_t ti_n3 = stage_tid(h_n3, lane);
+        const int4 tet_n2 = stage_tet(h_n2, lane, ti_n2);
+        const bool ok_n1 = stage_verts(h_n1, tet_n1, st ^ 1);   // vertices of ring g+1 -> the other stage
+        // ---- ring g: its vertices were requested one iteration ago
+        cp_async_wait<1>();
+        __syncwarp();
+        double acc[NRED];
+#pragma unroll
+        for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
+        if ((uint32_t)lane < h_cur.cnt && ok_cur) {
+            double x[12];
+            const double* srcv = vb + (size_t)st * 12 * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) x[k] = srcv[k * 32];
+            accumulate(x, acc);
+        }
+        for (uint32_t k = 32 + lane; k < h_cur.cnt; k += 32) {  // rings of more than 32 tets: the rest is fetched on demand
+            const int4 t = stage_tet(h_cur, k, stage_tid(h_cur, k));
+            int32_t a[4];
+            if (rotate(t, h_cur.c, a)) {
+                double x[12];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) gather_vertex(V, a[v], x + 3 * v);
+                accumulate(x, acc);
+            } else {
+                atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
+            }
+        }
+        __syncwarp();  // every lane has read stage `st` before the next iteration refills it
+        if (ENERGY_ONLY) {
+            double en = warp_sum(acc[0]);
+            if (lane == 0) {  // getNewEnergy :619-622
+                if (isinf(en) || isnan(en) || en <= 0.0 || en > TWG_MAX_ENERGY) en = TWG_MAX_ENERGY;
+                E[g] = en;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NRED; ++k) red[wib][k][lane] = acc[k];
+            __syncwarp();
+            const int cmp = lane & 15, half = lane >> 4;
+            double sum = 0.0;
+            if (cmp < NRED) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum += red[wib][cmp][half * 16 + j];
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+            __syncwarp();
+            bool bad = false;
+            if (cmp == 0) {
+                if (isinf(sum)) sum = TWG_MAX_ENERGY;
+                bad = isnan(sum) || sum <= 0.0;
+            } else if (cmp < NRED) {
+                bad = !isfinite(sum);
+            }
+            const bool good = !__any_sync(0xffffffffu, bad);
+            if (half == 0) {
+                if (cmp == 0) { E[g] = sum; if (ok) ok[g] = good ? 1 : 0; }
+                else if (cmp < 4) J3[g * 3 + (cmp - 1)] = sum;
+                else if (cmp < NRED) {
+                    const int s0 = (cmp == 4) ? 0 : (cmp == 5) ? 1 : (cmp == 6) ? 2 : (cmp == 7) ? 4 : (cmp == 8) ? 5 : 8;
+                    const int s1 = (cmp == 5) ? 3 : (cmp == 6) ? 6 : (cmp == 8) ? 7 : s0;
+                    double* Hg = H9 + g * 9;
+                    Hg[s0] = sum;
+                    Hg[s1] = sum;
+                }
+            }
+        }
+        // ---- advance the pipeline
+        h_cur = h_n1; ok_cur = ok_n1;
+        h_n1 = h_n2; tet_n1 = tet_n2;
+        h_n2 = h_n3; ti_n2 = ti_n3;
+        h_n3 = h_n4;
+        row_n4 = row_n5;
+        st ^= 1;
+    }
+    cp_async_wait<0>();
+}
+
+constexpr size_t kRingAsyncSmem = (size_t)8 * 2 * 12 * 32 * sizeof(double);  // 48 KiB of staged vertices per CTA
+
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
 int launch_soa(twg_ctx* c, const double* const dT[12], double* dE, double* dJ3, double* dH9, uint64_t n, cudaStream_t st) {
@@ -402,6 +587,24 @@ unsigned grid_for(twg_ctx* c, uint64_t items, int per_block, int waves) {
 // persistent grid of the ring kernels: 3 resident CTAs per SM (80 registers x 256 threads), every warp pipelines over its rings
 int ring_waves(const twg_ctx* c) { return c->opt.ring_waves; }
 
+template <bool ENERGY_ONLY>
+int launch_ring(twg_ctx* c, cudaStream_t st, const double* dV, uint32_t nV, const int4* dTets, uint64_t nT, const int32_t* dTids, const uint64_t* dOff,
+                const int32_t* dCenter, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk) {
+    if (c->opt.ring_async) {
+        static bool attr_set[64] = {false};  // per device: the 48 KiB of dynamic shared memory need the opt-in once
+        if (c->device < 64 && !attr_set[c->device]) {
+            TWG_CUDA(c, cudaFuncSetAttribute(amips_ring_async_kernel<ENERGY_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingAsyncSmem));
+            attr_set[c->device] = true;
+        }
+        TWG_LAUNCH(c, (amips_ring_async_kernel<ENERGY_ONLY>), grid_for(c, nG, 8, ring_waves(c)), 256, kRingAsyncSmem, st, dV, dTets, dTids, dOff, dCenter, dVids, nG,
+                   dE, dJ3, dH9, dOk, nV, nT, c->dcounters);
+        return 0;
+    }
+    TWG_LAUNCH(c, (amips_ring_kernel<ENERGY_ONLY>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids, nG, dE, dJ3, dH9, dOk, nV,
+               nT, c->dcounters);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -438,9 +641,7 @@ int twg_amips_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, const int3
     if (nG == 0) return 0;
     TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
-               dCenter, (const int32_t*)nullptr, nG, dE, dJ3, dH9, dOk, nV, nT, c->dcounters);
-    return 0;
+    return launch_ring<false>(c, pick(c, stream), dV, nV, (const int4*)dTets, nT, dTids, dOff, dCenter, (const int32_t*)nullptr, nG, dE, dJ3, dH9, dOk);
 }
 
 // one-rings named by their centre vertex: members of ring g are adj_tets[adj_off[v] .. adj_off[v+1]) with v = dVids[g]
@@ -452,9 +653,7 @@ int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, con
     if (nG == 0) return 0;
     TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<false>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, pick(c, stream), dV, (const int4*)dTets, dAdjTets, dAdjOff,
-               (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk, nV, nT, c->dcounters);
-    return 0;
+    return launch_ring<false>(c, pick(c, stream), dV, nV, (const int4*)dTets, nT, dAdjTets, dAdjOff, (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk);
 }
 
 int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dTids,
@@ -464,9 +663,8 @@ int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const i
     if (nG == 0) return 0;
     TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, (amips_ring_kernel<true>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, pick(c, stream), dV, (const int4*)dTets, dTids, dOff,
-               (const int32_t*)nullptr, (const int32_t*)nullptr, nG, dE, (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr, nV, nT, c->dcounters);
-    return 0;
+    return launch_ring<true>(c, pick(c, stream), dV, nV, (const int4*)dTets, nT, dTids, dOff, (const int32_t*)nullptr, (const int32_t*)nullptr, nG, dE,
+                             (double*)nullptr, (double*)nullptr, (uint8_t*)nullptr);
 }
 
 // ---- host-buffer entry points: chunked H2D -> kernel -> D2H pipeline over TWG_NUM_STREAMS streams ----

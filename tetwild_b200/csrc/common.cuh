@@ -20,16 +20,19 @@ struct twg_options {
     int env_front = 32;        // frontier cap of a group: 16 / 32 / 64
     int env_quorum = 16;       // parked lanes that trigger a leaf round
     int env_top = 64;          // pair records staged in shared memory
+    int env_bound = 1;         // oriented facet bound before the exact leaf routine
     int envelope_sort = 1;     // Morton-order large batches before traversal
     int sort_bits = 24;        // Morton bits that are sorted
     long long chunk_points = 1ll << 20;  // points per staging chunk of the host entry points
     int ring_waves = 3;        // resident CTAs per SM of the one-ring kernels
+    int ring_async = 1;        // one-ring kernels gather the vertices of the next ring with cp.async into shared memory
     int winding_minb = 3;
     int winding_sort = 1;
     int winding_leaf = 64;
     int winding_device_build = 1;
     int amips_tma = 1;
-    int nearest_mode = 1;      // 1: warp-cooperative kernel, 0: per-lane descents (round 1)
+    int nearest_mode = 1;      // 1: round-scheduled lanes, 2: packets + one query per warp, 0: per-lane descents (round 1)
+    int nearest_group = 64;    // queries per claimed group of the round-scheduled nearest kernel
     int nearest_budget = 96;   // node visits a packet of 32 queries may spend before its queries are finished one per warp
     int trace = 0;
 };
@@ -139,6 +142,14 @@ __device__ __forceinline__ double2 ld_stream2(const double* p) {
 __device__ __forceinline__ void st_stream2(double* p, double2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
+
+// ---- per-thread asynchronous global -> shared copies (LDGSTS): 8 bytes each, both addresses 8-byte aligned ----
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- mbarrier + 1-D bulk async copy (TMA) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -18,16 +18,19 @@ const OptDesc kOpts[] = {
     {"env_front", &twg_options::env_front, nullptr, 1, 64},
     {"env_quorum", &twg_options::env_quorum, nullptr, 1, 32},
     {"env_top", &twg_options::env_top, nullptr, 4, 512},
+    {"env_bound", &twg_options::env_bound, nullptr, 0, 1},
     {"envelope_sort", &twg_options::envelope_sort, nullptr, 0, 1},
     {"sort_bits", &twg_options::sort_bits, nullptr, 8, 30},
     {"chunk_points", nullptr, &twg_options::chunk_points, 1024, 1ll << 31},
     {"ring_waves", &twg_options::ring_waves, nullptr, 1, 32},
+    {"ring_async", &twg_options::ring_async, nullptr, 0, 1},
     {"winding_minb", &twg_options::winding_minb, nullptr, 1, 8},
     {"winding_sort", &twg_options::winding_sort, nullptr, 0, 1},
     {"winding_leaf", &twg_options::winding_leaf, nullptr, 2, 4096},
     {"winding_device_build", &twg_options::winding_device_build, nullptr, 0, 1},
     {"amips_tma", &twg_options::amips_tma, nullptr, 0, 1},
-    {"nearest_mode", &twg_options::nearest_mode, nullptr, 0, 1},
+    {"nearest_mode", &twg_options::nearest_mode, nullptr, 0, 2},
+    {"nearest_group", &twg_options::nearest_group, nullptr, 32, 4096},
     {"nearest_budget", &twg_options::nearest_budget, nullptr, 1, 1 << 30},
     {"trace", &twg_options::trace, nullptr, 0, 1},
 };

@@ -80,7 +80,7 @@ __device__ __noinline__ bool env_overflow_fallback(const SurfaceView& S, tw::V3 
 template <int MINB, int FM>
 __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceView S, const double* __restrict__ P, const uint32_t* __restrict__ perm,
                                                                 uint64_t n, double eps2, uint8_t* __restrict__ out, unsigned long long* counter, int group, int policy, int kLeafQuorum,
-                                                                unsigned long long* dbg) {
+                                                                unsigned long long* dbg, int use_bound) {
     static_assert(FM <= kEnvStack, "the frontier of a group must fit the per-lane stack");
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
@@ -228,10 +228,21 @@ __global__ void __launch_bounds__(kEnvThreads, MINB) env_points_kernel(SurfaceVi
         }
         if (policy == 0 ? (n_pend >= kLeafQuorum || pend == act) : (n_pend >= kLeafQuorum || n_pend >= n_step)) {
             if (active && pend_mask != 0) {
-                const int c = __ffs(pend_mask) - 1;
-                pend_mask &= pend_mask - 1;
-                const uint32_t pos = pend_c0 + (uint32_t)c - leaf0;
-                if (pos < S.nF) {
+                // the lane's next parked facet whose ORIENTED bound (surface.cuh::TriBound, ~20 FP64 instructions) is within eps: a
+                // leaf box admits every facet whose axis-aligned extent comes within eps of the query, the plane of most of them
+                // does not -- those never reach the ~170-instruction exact routine
+                uint32_t pos = 0;
+                bool have = false;
+                while (pend_mask != 0) {
+                    const int c = __ffs(pend_mask) - 1;
+                    pend_mask &= pend_mask - 1;
+                    pos = pend_c0 + (uint32_t)c - leaf0;
+                    if (pos >= S.nF) continue;
+                    if (!use_bound) { have = true; break; }
+                    const TriBound tb = twd::load_bound(S.tb + pos);
+                    if (twd::bound_lb2(tb, p) <= eps2 * twd::kSlack) { have = true; break; }
+                }
+                if (have) {
                     double s, t; tw::V3 nd; bool deg;
                     if (twd::facet_d2(S, pos, p, s, t, nd, deg) <= eps2) { out[src] = 0; active = false; pend_mask = 0; }
                 }
@@ -639,6 +650,188 @@ __global__ void __launch_bounds__(kEnvThreads, 6) nearest_packet_kernel(SurfaceV
     }
 }
 
+// Exact nearest facet, form (3): ROUND-SCHEDULED lanes -- the machinery of env_points_kernel applied to the full search. One
+// query per lane, but no lane ever runs the long routines alone:
+//   * persistent warps claim groups of consecutive Morton-sorted queries; a lane that finishes takes the next query of the
+//     group at once, so a far query (10-100x the work of a near one) delays nobody;
+//   * every round the warp runs ONE phase for all lanes that are ready for it: REFILL (start queries on idle lanes), LEAF (one
+//     exact point-triangle test per parked lane) or STEP (pop a subtree, bound its eight descendants with one 192-byte run) --
+//     the phase with the most lanes ready;
+//   * a lane that reaches facets parks them; in the LEAF phase it first drops parked facets whose ORIENTED bound
+//     (tw_math.cuh::TriBound) cannot beat its current best, and only runs the exact routine on the rest (~1 in 10 for far
+//     queries);
+//   * the per-lane stack holds (node, lower bound) pairs and is re-checked when popped, nearest descendant on top; the first
+//     thing a query tests is the facet that answered the lane's previous query (nearest_facet_with_hint, mesh_AABB.h:162-176),
+//     so the search starts with a bound that is already within a facet or two of the answer.
+// Unlike the packet form, a lane only ever looks at ITS OWN candidates: far queries of one warp lie ~0.02 apart (their density
+// is low) and share few of them. The stack cannot overflow for heaps of up to 2^24 leaves (7 per 8-wide level + the root level);
+// deeper heaps that do are finished by the exact binary descent twd::nearest_facet. Result: the exact minimum over all facets.
+constexpr int kNrStack = 64;
+
+template <int MINB>
+__global__ void __launch_bounds__(kEnvThreads, MINB) nearest_rounds_kernel(SurfaceView S, const double* __restrict__ Ps /*sorted*/, const uint32_t* __restrict__ perm,
+                                                                       uint64_t n, uint32_t* __restrict__ facet, double* __restrict__ nearest,
+                                                                       double* __restrict__ d2out, unsigned long long* counter, int group, int quorum,
+                                                                       unsigned long long* dbg /*NULL unless option trace: work counters 3..6*/) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    NodePair* top = reinterpret_cast<NodePair*>(smraw);
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t topN = stage_top(S, top, &bar);
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t leaf0 = S.nLeafP;
+    const int L = 31 - __clz(leaf0);
+    const uint32_t first = 1u << (L % 3);
+    const float fmax_ = __int_as_float(0x7f7fffff);
+    uint32_t n_steps = 0, n_bounds = 0, n_exact = 0, n_rounds = 0;
+    uint64_t cb = 0, ce = 0;
+    bool more = true, active = false, hint_pending = false;
+    uint32_t pend_mask = 0, pend_c0 = 0, hint = TWG_NO_FACET;
+    tw::V3 p = tw::mk(0, 0, 0);
+    twd::PointF q = twd::bracket(p);
+    uint64_t src = 0;
+    double bd2 = DBL_MAX, bs = 0.0, bt = 0.0;
+    uint32_t bpos = 0;
+    float thr = fmax_;
+    uint32_t stk[kNrStack];
+    float stl[kNrStack];
+    int sp = 0;
+    for (;;) {
+        const unsigned need = __ballot_sync(full, !active);
+        const unsigned act = ~need;
+        const unsigned pend = __ballot_sync(full, active && (pend_mask != 0 || hint_pending));
+        const int n_pend = __popc(pend), n_step = __popc(act & ~pend);
+        const bool can_refill = need != 0 && (cb < ce || more);
+        if (act == 0 && !can_refill) break;
+        const int n_need = can_refill ? __popc(need) : 0;
+        ++n_rounds;
+        if (n_need > 0 && (act == 0 || (n_need >= n_pend && n_need >= n_step))) {
+            // ---- REFILL
+            if (cb >= ce && more) {
+                unsigned long long c = 0;
+                if (lane == 0) c = atomicAdd(counter, 1ull);
+                c = __shfl_sync(full, c, 0);
+                cb = c * (uint64_t)group;
+                ce = (cb + group < n) ? cb + group : n;
+                if (cb >= n) { more = false; cb = ce = 0; }
+            }
+            if (cb < ce) {
+                const uint64_t mine = cb + __popc(need & lt);
+                if (!active && mine < ce) {
+                    src = mine;
+                    p = tw::mk(__ldg(Ps + 3 * mine), __ldg(Ps + 3 * mine + 1), __ldg(Ps + 3 * mine + 2));
+                    q = twd::bracket(p);
+                    bd2 = DBL_MAX; bs = bt = 0.0; bpos = 0; thr = fmax_;
+                    sp = 0;
+                    for (uint32_t k = 0; k < first; ++k) { stk[sp] = first + k; stl[sp] = 0.f; ++sp; }
+                    pend_mask = 0;
+                    hint_pending = hint != TWG_NO_FACET;
+                    active = true;
+                }
+                const uint64_t adv = cb + __popc(need);
+                cb = adv < ce ? adv : ce;
+            }
+            continue;
+        }
+        if (n_pend >= quorum || n_pend >= n_step) {
+            // ---- LEAF: one exact test per parked lane; facets whose oriented bound cannot win are dropped first
+            if (active && (hint_pending || pend_mask != 0)) {
+                uint32_t pos = 0;
+                bool have = false;
+                if (hint_pending) {
+                    pos = hint; hint_pending = false; have = true;
+                } else {
+                    while (pend_mask != 0) {
+                        const int c = __ffs(pend_mask) - 1;
+                        pend_mask &= pend_mask - 1;
+                        pos = pend_c0 + (uint32_t)c - leaf0;
+                        if (pos >= S.nF) continue;
+                        const TriBound tb = twd::load_bound(S.tb + pos);
+                        ++n_bounds;
+                        if (twd::bound_lb2(tb, p) <= bd2 * twd::kSlack) { have = true; break; }
+                    }
+                }
+                if (have) {
+                    double s_, t_; tw::V3 nd; bool deg;
+                    const double d2 = twd::facet_d2(S, pos, p, s_, t_, nd, deg);
+                    ++n_exact;
+                    if (d2 < bd2) {
+                        bd2 = d2; bs = s_; bt = t_; bpos = pos;
+                        thr = (bd2 < 1e37) ? __double2float_ru(bd2 * twd::kSlack) : fmax_;
+                    }
+                }
+            }
+            continue;
+        }
+        // ---- STEP
+        if (active && pend_mask == 0 && !hint_pending) {
+            uint32_t node = 0;
+            bool got = false;
+            while (sp > 0) {
+                --sp;
+                if (stl[sp] <= thr) { node = stk[sp]; got = true; break; }
+            }
+            if (!got) {
+                // ---- the query is finished: results to the caller's position
+                const uint64_t i = perm ? (uint64_t)__ldg(perm + src) : src;
+                if (d2out) d2out[i] = bd2;
+                if (facet || nearest) {
+                    const tw::TriRec r = twd::load_tri(S.tris + bpos);
+                    if (facet) facet[i] = r.facet;
+                    if (nearest) {
+                        tw::V3 pt;
+                        if (r.flags & 1u) {
+                            double tv[9];
+#pragma unroll
+                            for (int k = 0; k < 9; ++k) tv[k] = __ldg(S.triV + (size_t)bpos * 9 + k);
+                            tw::tri_sqdist_degenerate(p, tv, pt);
+                        } else {
+                            pt = tw::tri_nearest_point(r, bs, bt);
+                        }
+                        nearest[3 * i] = pt.x; nearest[3 * i + 1] = pt.y; nearest[3 * i + 2] = pt.z;
+                    }
+                }
+                hint = bpos;
+                active = false;
+            } else {
+                float d[8];
+                const uint32_t mask = twd::wide_step(S, q, thr, node, top, topN, d);
+                ++n_steps;
+                const uint32_t c0 = 8u * node;
+                if (c0 >= leaf0) {
+                    pend_mask = mask; pend_c0 = c0;
+                } else if (mask != 0) {
+                    if (sp + 8 > kNrStack) {
+                        // (heaps deeper than 2^24 leaves only) finish this query with the exact binary descent
+                        twd::Nearest nb;
+                        nb.d2 = bd2; nb.s = bs; nb.t = bt; nb.pos = bpos; nb.deg = false; nb.pt_deg = p;
+                        twd::nearest_facet(S, p, nb, top, topN);
+                        bd2 = nb.d2; bs = nb.s; bt = nb.t; bpos = nb.pos;
+                        sp = 0;
+                    } else {
+                        int best = -1;
+                        float bdm = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            if (((mask >> c) & 1u) && (best < 0 || d[c] < bdm)) { best = c; bdm = d[c]; }
+#pragma unroll
+                        for (int c = 7; c >= 0; --c)
+                            if (((mask >> c) & 1u) && c != best) { stk[sp] = c0 + (uint32_t)c; stl[sp] = d[c]; ++sp; }
+                        stk[sp] = c0 + (uint32_t)best; stl[sp] = bdm; ++sp;  // nearest descendant is popped first
+                    }
+                }
+            }
+        }
+    }
+    if (dbg) {  // diagnostics (option trace): 3 = 8-wide steps, 4 = oriented bounds, 5 = exact tests, 6 = warp rounds
+        atomicAdd(dbg + 3, (unsigned long long)n_steps);
+        atomicAdd(dbg + 4, (unsigned long long)n_bounds);
+        atomicAdd(dbg + 5, (unsigned long long)n_exact);
+        if (lane == 0) atomicAdd(dbg + 6, (unsigned long long)n_rounds);
+    }
+}
+
 // one sample of isFaceOutEnvelop_sampling (:1079-1093): hint facet first, then the tree. Returns true if OUT.
 __device__ __forceinline__ bool sample_out(const SurfaceView& S, tw::V3 p, double eps2, uint32_t& prev, const NodePair* top, uint32_t topN) {
     if (prev != TWG_NO_FACET) {
@@ -1002,11 +1195,11 @@ int twg_envelope_points_out_dev(twg_surface* s, const double* dP, uint64_t n, do
     const int group = c->opt.env_group, policy = c->opt.env_policy, front = c->opt.env_front, quorum = c->opt.env_quorum;
     const unsigned grid = grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 8);
     if (front <= 16)
-        TWG_LAUNCH(c, (env_points_kernel<8, 16>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters);
+        TWG_LAUNCH(c, (env_points_kernel<8, 16>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters, c->opt.env_bound);
     else if (front >= 64)
-        TWG_LAUNCH(c, (env_points_kernel<8, 64>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters);
+        TWG_LAUNCH(c, (env_points_kernel<8, 64>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters, c->opt.env_bound);
     else
-        TWG_LAUNCH(c, (env_points_kernel<8, 32>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters);
+        TWG_LAUNCH(c, (env_points_kernel<8, 32>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, eps2, dOut, lane->counters, group, policy, quorum, c->dcounters, c->opt.env_bound);
     return twg_lane_mark(c, lane);
 }
 
@@ -1024,7 +1217,14 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     const bool sorted = n >= TWG_SORT_MIN && c->opt.envelope_sort;
     if (sorted) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box, &Pq));
     TWG_CUDA(c, cudaMemsetAsync(lane->counters, 0, sizeof(unsigned long long), st));
-    if (sorted && c->opt.nearest_mode == 1 && s->nLeafP >= 8) {  // packets of 32 neighbouring queries share one traversal
+    if (sorted && c->opt.nearest_mode == 1 && s->nLeafP >= 8) {  // round-scheduled lanes (form 3)
+        const int group = c->opt.nearest_group;
+        const unsigned grid = grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 6);
+        TWG_LAUNCH(c, (nearest_rounds_kernel<6>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, dFacet, dNearest, dD2, lane->counters, group,
+                   c->opt.env_quorum, c->opt.trace ? c->dcounters : (unsigned long long*)nullptr);
+        return twg_lane_mark(c, lane);
+    }
+    if (sorted && c->opt.nearest_mode == 2 && s->nLeafP >= 8) {  // packets of 32 neighbouring queries share one traversal
         const uint64_t claims = ((n + 31) / 32 + kPacketChunk - 1) / kPacketChunk;
         TWG_LAUNCH(c, nearest_packet_kernel, grid_persistent(c, claims, kEnvThreads / 32, 6), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, dFacet,
                    dNearest, dD2, lane->counters, c->opt.nearest_budget);

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) qs_row_scan_kernel(uint32_t* __restrict__
 // One pass over one tile: stable ranks by digit, staging in digit order, contiguous runs out.
 //   FIRST: the pairs' indices are implicit (position in the batch); LAST with Pin: write the POINTS in sorted order + perm
 template <bool FIRST>
-__global__ void __launch_bounds__(kSortThreads) qs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n,
+__global__ void __launch_bounds__(kSortThreads, 4) qs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t n,
                                                               const uint32_t* __restrict__ hist /*scanned rows*/, const uint32_t* __restrict__ total, uint32_t ntiles,
                                                               Digit dg, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                                                               const double* __restrict__ Pin, double* __restrict__ Pout) {
@@ -179,13 +179,12 @@ __global__ void __launch_bounds__(kSortThreads) qs_scatter_kernel(const uint32_t
 #pragma unroll
     for (int k = 0; k < kSortWarps; ++k) cnt[k][threadIdx.x] = 0;
     __syncthreads();
-    uint32_t key[kSortItems], val[kSortItems], rank[kSortItems];
+    uint32_t key[kSortItems];
+    uint16_t rank[kSortItems];  // < 512: position among the warp's elements with the same digit
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
         const uint32_t e = tile_elem(w, r, l);
-        const bool valid = e < tile_n;
-        key[r] = valid ? __ldg(keys_in + base + e) : 0xffffffffu;
-        val[r] = FIRST ? (uint32_t)(base + e) : (valid ? __ldg(vals_in + base + e) : 0u);
+        key[r] = e < tile_n ? __ldg(keys_in + base + e) : 0xffffffffu;
     }
     // ---- stable rank inside the warp's 512 elements: round after round, lanes with equal digits form a group; the first lane of the
     // group reads and advances the warp's counter of that digit, the others add their position in the group
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(kSortThreads) qs_scatter_kernel(const uint32_t
             cnt[w][d] = b + (uint32_t)__popc(m);
         }
         b = __shfl_sync(full, b, leader);
-        rank[r] = b + (uint32_t)__popc(m & lt);
+        rank[r] = (uint16_t)(b + (uint32_t)__popc(m & lt));
         __syncwarp();
     }
     __syncthreads();
@@ -233,14 +232,15 @@ __global__ void __launch_bounds__(kSortThreads) qs_scatter_kernel(const uint32_t
         gbase[d] = (wo2 + ti - tv) + __ldg(hist + (size_t)d * ntiles + blockIdx.x);
     }
     __syncthreads();
-    // ---- stage the tile in digit order
+    // ---- stage the tile in digit order (the indices are only read now: they are not live across the ranking rounds)
 #pragma unroll
     for (int r = 0; r < kSortItems; ++r) {
-        if (tile_elem(w, r, l) < tile_n) {
+        const uint32_t e = tile_elem(w, r, l);
+        if (e < tile_n) {
             const uint32_t d = dg.of(key[r]);
-            const uint32_t slot = dstart[d] + cnt[w][d] + rank[r];
+            const uint32_t slot = dstart[d] + cnt[w][d] + (uint32_t)rank[r];
             skey[slot] = key[r];
-            sval[slot] = val[r];
+            sval[slot] = FIRST ? (uint32_t)(base + e) : __ldg(vals_in + base + e);
         }
     }
     __syncthreads();
