@@ -32,15 +32,16 @@ import numpy as np  # noqa: E402
 
 FULL = {"envelope": 10_000_000, "amips": 50_000_000, "amips_literal": 50_000_000, "amips_ring": 50_000_000, "winding": 100_000_000, "winding_oneshot": 100_000_000,
         "envelope_faces": 400_000, "envelope_faces_c1": 100_000, "nearest": 10_000_000, "amips_quality": 50_000_000,
-        "envelope_strong": 10_000_000, "winding_strong": 100_000_000}
+        "envelope_strong": 10_000_000, "winding_strong": 100_000_000, "pass_stream": 30_000}
 UNIT = {"envelope": "points/s", "amips": "tets/s", "amips_literal": "tets/s", "amips_ring": "tets/s", "winding": "queries/s", "winding_oneshot": "queries/s",
         "envelope_faces": "faces/s", "envelope_faces_c1": "faces/s", "nearest": "points/s", "amips_quality": "tets/s",
-        "envelope_strong": "points/s", "winding_strong": "queries/s"}
+        "envelope_strong": "points/s", "winding_strong": "queries/s", "pass_stream": "calls/s"}
 METRIC = {"envelope": "envelope points/s", "amips": "AMIPS E+J+H tet-evals/s", "amips_literal": "AMIPS E+J+H tet-evals/s (literal C3)",
           "amips_ring": "AMIPS one-ring E+J+H tet-evals/s", "winding": "winding-number queries/s",
           "winding_oneshot": "winding-number queries/s, one shot (hierarchy build + evaluation + decision, InoutFiltering::filter)",
           "envelope_faces": "envelope faces/s (isFaceOutEnvelop)", "envelope_faces_c1": "envelope faces/s (isFaceOutEnvelop, faces of edge diag/20)",
           "nearest": "nearest-facet projections/s", "amips_quality": "AMIPS tet-quality evals/s (calTetQualities)",
+          "pass_stream": "scheduler-shaped call stream, hot-path calls/s (one pass of MeshRefinement::doOperations)",
           "envelope_strong": "envelope points/s, fixed batch split by index over the ranks", "winding_strong": "winding-number queries/s, fixed batch split by index over the ranks"}
 FACE_EDGE = 0.02     # C1-shaped candidate faces: small enough that the flat face stays within eps of the curved icosphere about half the time
 FACE_EDGE_C1 = 0.05  # the edge SURVEY.md 8d states for C1 (diag/20): ~1.4 k samples per face
@@ -56,6 +57,7 @@ WORKLOAD = {
     "amips_quality": "C3 indexed layout: calTetQualities over %d random non-degenerate tets (int4 tet -> 4 gathered vertices, exact orientation gate, energy, MAX_ENERGY rules of LocalOperations.cpp:862-884) on the resident tet mesh, FP64",
     "nearest": "C2 points, full nearest search: %d points vs 200000-triangle torus knot -> nearest facet id + nearest point + d2 (nearest_facet, mesh_AABB.h:130-176; the projection callers VertexSmoother.cpp:354-362, Preprocess.cpp:529)",
     "envelope_faces": "C1-shaped call stream: %d candidate faces (edge ~ diag/50, sampled on the device at sampling_dist = 1e-3 diag like Common.cpp:143-255) vs the 20480-triangle icosphere, eps through State.cpp:36-41",
+    "pass_stream": "C1 proxy: a generated pass-shaped stream of ~%d hot-path calls on the 20480-triangle icosphere and a 16 k-tet mesh (tetwild_b200/callstream.py: the call mix of split / collapse / smooth candidates, MeshRefinement.cpp:120-183) -- no TetWild binary can be built here to record a real one",
     "envelope_faces_c1": "C1 at its stated size: %d candidate faces of edge ~ diag/20 (~1.4 k samples each at sampling_dist = 1e-3 diag) vs the 20480-triangle icosphere, eps through State.cpp:36-41",
 }
 L2NOTE = {
@@ -71,15 +73,16 @@ L2NOTE = {
     "winding": "inputs larger than L2: 24 B per query per step (2.4 GB at full size); the ~210 MB hierarchy is re-read from L2/HBM",
     "winding_strong": "inputs larger than L2: 24 B per query (2.4 GB over the ranks); the ~210 MB hierarchy is re-read from L2/HBM",
     "winding_oneshot": "one call per step: 2.4 GB of host queries + the surface in, 100 MB of decisions out",
+    "pass_stream": "n/a: latency-bound host round trips (call by call) or a handful of small batches (re-batched)",
 }
 # algorithmic HBM bytes per unit. ring: 16 B indices + 72 B of unshared gathered vertices + (24 B centre + 105 B results) / 24;
 # quality: 16 B tet + 72 B of unshared vertices + 24 B / 24 of the shared centre + 8 B out (what ncu measures: 97 B/tet)
 ALG_BYTES = {"envelope": 25.0, "amips": 200.0, "amips_literal": 200.0, "amips_ring": 93.0, "winding": 25.0, "envelope_faces": 73.0, "envelope_faces_c1": 73.0,
-             "nearest": 60.0, "amips_quality": 97.0, "envelope_strong": 25.0, "winding_strong": 25.0, "winding_oneshot": 25.0}
+             "nearest": 60.0, "amips_quality": 97.0, "envelope_strong": 25.0, "winding_strong": 25.0, "winding_oneshot": 25.0, "pass_stream": 0.0}
 # what binds the dominant kernel of each part (from the committed ncu captures, profiles/): HBM bandwidth, L1 / LSU throughput of
 # the divergent tree walks, or the FP64 pipe
 BOUND = {"envelope": "l1", "envelope_strong": "l1", "envelope_faces": "l1", "envelope_faces_c1": "l1", "nearest": "l1", "amips": "hbm", "amips_literal": "hbm",
-         "amips_quality": "hbm", "amips_ring": "hbm", "winding": "fp64", "winding_strong": "fp64", "winding_oneshot": "fp64"}
+         "amips_quality": "hbm", "amips_ring": "hbm", "winding": "fp64", "winding_strong": "fp64", "winding_oneshot": "fp64", "pass_stream": "latency"}
 SM_COUNT, L1_BYTES_PER_CLK = 148, 128   # B200: 148 SMs, 128 B/clk/SM of L1 (l1tex) bandwidth
 
 
@@ -348,6 +351,17 @@ def cpu_workload(part, n_full):
         return run, 2000, ("reference" if have_ref else "port"), (
             "reference sampleTriangle (Common.cpp:143-255) + DistanceQuery.h + mesh_AABB.cpp compiled unmodified, composed by the loop of LocalOperations.cpp:1046-1109 (oracle/ref_wrap.cpp)"
             if have_ref else "oracle port of isFaceOutEnvelop_sampling (LocalOperations.cpp:1046-1109)") + ", first OUT sample stops the face, OpenMP over faces"
+    if base == "pass_stream":
+        from tetwild_b200 import callstream as cs
+        cache = {}
+
+        def run(m, threads):
+            if "s" not in cache:
+                cache["s"] = cs.make_pass_stream(*stream_sizes(n_full), seed=1)
+                cache["r"] = cs.CpuReplayer(O, cache["s"])
+            m = min(m, len(cache["s"]["calls"]))
+            return cache["r"].call_by_call(limit=m)[0]
+        return run, 2000, "port", "oracle, ONE call at a time on ONE core (how the reference's sequential scheduler runs; Python ctypes call overhead included, as in the GPU arm)"
     if base in ("winding", "winding_oneshot"):
         V, F = sphere_surface()
         state = {}
@@ -373,11 +387,19 @@ def cpu_workload(part, n_full):
     raise ValueError(part)
 
 
+def stream_sizes(n_calls):
+    """(collapse, smooth, split) candidates that give about n_calls calls (~3.5 calls per candidate)"""
+    k = max(30, int(n_calls / 3.5 / 8))
+    return 3 * k, 3 * k, 2 * k
+
+
 def cpu_rate(part, n_full, threads, budget_s=8.0, modes=False):
     """Times the reference CPU path of one part on a bounded sample. -> dict for the JSON line's cpu_baseline."""
     import oracle as O
     O.build()
     run, probe, kind, what = cpu_workload(part, n_full)
+    if part == "pass_stream":
+        threads, modes = 1, False      # sequential by construction
     probe = min(probe, n_full)
     r0 = probe / run(probe, threads)
     m = int(min(n_full, 20_000_000, max(probe, r0 * budget_s)))
@@ -615,6 +637,8 @@ def run_gpu(args, parts):
             for k in ("l1tex_throughput_pct", "lts_throughput_pct", "issue_active_pct", "lanes_per_inst"):
                 if k in t:
                     r[k + "_ncu"] = t[k]
+        elif bound == "latency":
+            r.update({"achieved": None, "peak": None, "unit": None, "frac": None, "note": "host round trips: no device roofline applies"})
         elif bound == "fp64":
             if "fp64_inst" in t:
                 flops = t["fp64_inst"] / t["units"] * 64.0 * n / (kms * 1e-3) / 1e12   # one FP64-pipe warp instruction = 32 lanes x (1 DFMA = 2 flops)
@@ -939,6 +963,37 @@ def run_gpu(args, parts):
             roof_extra = {"pairs_per_query": pairs_per_query,
                           "pairs_note": "(query, cap point or leaf facet) evaluations per query, counted by the kernel itself (twg_debug_counter 2)"}
             del dQ, dK, Wt, pipe
+        elif part == "pass_stream":
+            from tetwild_b200 import callstream as cs
+            strm = cs.make_pass_stream(*stream_sizes(n), seed=1)
+            ncalls = len(strm["calls"])
+            counts, units = cs.mix(strm)
+            G = cs.GpuReplayer(ctx, strm)
+            G.batched(); G.call_by_call()                      # warm-up (scratch, pinned slabs, ring build)
+            barrier()
+            l0 = ctx.launches
+            t0 = time.perf_counter()
+            K, Wm = min(args.steps, 3), 1
+            tb = [G.batched() for _ in range(K)]
+            t1 = time.perf_counter()
+            ta, ra = G.call_by_call()
+            launches = ctx.launches - l0
+            win = (t0, t1)
+            rb = tb[-1][1]
+            bsec = float(np.median([x[0] for x in tb]))
+            mism = None
+            if rank == 0:
+                tc, rc = cs.CpuReplayer(O, strm).call_by_call()
+                mism = {"call_by_call_vs_batched": int(sum(not cs.same(k, ra[i], rb[i], tol=1e-12) for i, (k, _) in enumerate(strm["calls"]))),
+                        "gpu_vs_oracle": int(sum(not cs.same(k, ra[i], rc[i]) for i, (k, _) in enumerate(strm["calls"])))}
+            G.close()
+            units_per_step = ncalls * world
+            ms = kms = bsec * 1e3
+            e2e_s = bsec
+            res.update({"h2d": 0, "d2h": 0, "extra": {"calls": ncalls, "call_mix": counts, "units": units, "mismatches": mism,
+                                                     "rebatched_by_kind_calls_per_s": ncalls / bsec,
+                                                     "call_by_call_calls_per_s": ncalls / ta, "call_by_call_us_per_call": ta / ncalls * 1e6,
+                                                     "value_is": "the stream re-batched by kind through the host-buffer C ABI (7 calls per pass); call by call is reported beside it; both include the Python ctypes call overhead"}})
         elif part == "winding_oneshot":
             # InoutFiltering::filter as the reference calls it (InoutFiltering.cpp:40-52): surface + all centroids in, decisions out,
             # ONE call: hierarchy build + H2D + evaluation + D2H + the all-removed check. The device-resident `value` of this part is
@@ -1030,9 +1085,9 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.parts == "auto":
-        args.parts = "envelope,envelope_faces,envelope_faces_c1,nearest,amips,amips_literal,amips_quality,amips_ring,winding,winding_oneshot"
+        args.parts = "envelope,envelope_faces,envelope_faces_c1,nearest,amips,amips_literal,amips_quality,amips_ring,winding,winding_oneshot,pass_stream"
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            args.parts = args.parts.replace(",winding_oneshot", "") + ",envelope_strong,winding_strong"
+            args.parts = args.parts.replace(",winding_oneshot,pass_stream", "") + ",envelope_strong,winding_strong"
     parts = [p for p in args.parts.split(",") if p in FULL]
     if args.impl == "reference":
         run_reference(args, parts)

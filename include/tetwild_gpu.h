@@ -67,7 +67,7 @@ int twg_synchronize(twg_ctx* ctx);
 uint64_t twg_launch_count(const twg_ctx* ctx);  /* kernels launched by this context so far */
 const char* twg_version(void);
 /* Tuning knobs, per context (defaults: environment variable TWG_<NAME> read once at twg_create). Names: env_group, env_policy,
- * env_front, env_quorum, env_top, env_bound, envelope_sort, sort_bits, chunk_points, ring_waves, ring_async, winding_minb, winding_sort,
+ * env_front, env_quorum, env_top, env_bound, envelope_sort, surface_order, sort_bits, sort_curve, chunk_points, ring_waves, ring_prefetch, ring_minb, winding_minb, winding_sort,
  * winding_leaf, winding_device_build, amips_tma, nearest_mode, nearest_group, nearest_budget, trace. Values are clamped to their valid range. */
 int twg_set_option(twg_ctx* ctx, const char* name, double value);
 int twg_get_option(const twg_ctx* ctx, const char* name, double* value);
@@ -187,6 +187,11 @@ int twg_mesh_vertex_ring_ejh_dev(twg_mesh* m, const int32_t* dVids, uint64_t n, 
 int twg_mesh_ring_ejh(twg_mesh* m, const int32_t* t_ids, const uint64_t* group_off, const int32_t* center, uint64_t nGroups,
                       double* E, double* J3, double* H9, uint8_t* ok);
 int twg_mesh_ring_energy(twg_mesh* m, const int32_t* t_ids, const uint64_t* group_off, uint64_t nGroups, double* E);
+/* the smoother's line search (VertexSmoother.cpp:505-541: move v, getNewEnergy(conn_tets[v]), move it back) for n (vertex, trial
+ * position) pairs at once: E[i] = getNewEnergy of the one-ring of v_ids[i] with that vertex at xyz[i]. The resident mesh is not
+ * modified, so the pairs are independent: all step sizes of one Newton step, or the steps of many candidates, in one call. */
+int twg_mesh_vertex_trial_energy(twg_mesh* m, const int32_t* v_ids, const double* xyz, uint64_t n, double* E);
+int twg_mesh_vertex_trial_energy_dev(twg_mesh* m, const int32_t* dVids, const double* dXyz, uint64_t n, double* dE, void* stream);
 
 /* ---- S4: generalized winding number ------------------------------------------------------------------------------ */
 /* F may contain repeated faces (InoutFiltering.cpp:99-100). */

@@ -13,6 +13,7 @@ P = b.envelope_points_fast(V, F, n, eps, seed=1)
 for what, sel in (("all", slice(None)), ("near", None), ("far", None)):
     c = tw.Context(0)
     c.set_option("trace", 1)
+    c.set_option("nearest_mode", 2)   # the round-scheduled kernel carries the counters
     S = tw.Surface(c, V, F)
     if sel is None:
         d = S.squared_distance(P)

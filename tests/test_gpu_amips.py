@@ -119,10 +119,10 @@ def test_large_batch_properties(ctx, oracle):
     assert max(amips_close(T, (E2, J2, H2), (E, J, H))) < 1e-9
 
 
-def test_ring_kernels_async_gather_equals_direct_gather():
-    """The one-ring kernels stage the vertices of the next ring in shared memory with cp.async (amips_ring_async_kernel, the
-    default); option ring_async = 0 runs the round-1 kernel that gathers them into registers. Same members per lane, same
-    reduction order: bit-identical results, including rings of more than 32 tets, rejected rings and t_ids indirection."""
+def test_ring_kernels_prefetching_pipeline_equals_round1_kernel():
+    """Option ring_prefetch = 1 runs the one-ring kernel that prefetches the vertices of the next ring into L2 one pipeline stage
+    ahead (amips_ring_pf_kernel; measured slower, kept as an option); the default is the round-1 pipeline. Same members per lane, same reduction order: bit-identical
+    results, including rings of more than 32 tets, rejected rings and t_ids indirection."""
     import tetwild_b200 as tw
     V, tets, off, center = synth.ring_groups(5000, seed=21, kmin=3, kmax=70, scale_lo=0.1, scale_hi=10)
     V = V.copy()
@@ -133,7 +133,7 @@ def test_ring_kernels_async_gather_equals_direct_gather():
     res = []
     for mode in (1, 0):
         c = tw.Context(0)
-        c.set_option("ring_async", mode)
+        c.set_option("ring_prefetch", mode)
         a = c.amips_ring_ejh(V, tets, off, center)
         b = c.amips_ring_ejh(V, tets[perm], off, center, t_ids=inv.astype(np.int32))
         e = c.amips_ring_energy(V, tets, off)

@@ -473,6 +473,16 @@ class TetMesh:
         self.ctx._check(self._L.twg_mesh_ring_ejh(self.h, _ptr(tid), _ptr(off), _ptr(center), C.c_uint64(g), _ptr(E), _ptr(J), _ptr(H), _ptr(ok)))
         return E, J, H, ok
 
+    def vertex_trial_energy(self, v_ids, xyz):
+        """getNewEnergy of the one-ring of v_ids[i] with that vertex at xyz[i] (the smoother's line search, VertexSmoother.cpp:505-541);
+        the resident mesh is not modified"""
+        ids = np.ascontiguousarray(v_ids, dtype=np.int32)
+        xyz = _f64(xyz).reshape(-1, 3)
+        assert len(ids) == len(xyz)
+        E = np.empty(len(ids))
+        self.ctx._check(self._L.twg_mesh_vertex_trial_energy(self.h, _ptr(ids), _ptr(xyz), C.c_uint64(len(ids)), _ptr(E)))
+        return E
+
     def ring_energy(self, t_ids, group_off):
         tid = np.ascontiguousarray(t_ids, dtype=np.int32)
         off = np.ascontiguousarray(group_off, dtype=np.uint64)

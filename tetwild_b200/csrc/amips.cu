@@ -209,12 +209,13 @@ struct RingHead {   // stage result: CSR bounds and centre of one ring (member o
     int32_t c;
 };
 
-template <bool ENERGY_ONLY>
-__global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
+template <bool ENERGY_ONLY, int MINB>
+__global__ void __launch_bounds__(256, MINB) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
                                                             const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
                                                             const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
                                                             double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
-                                                            uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg) {
+                                                            uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg,
+                                                            const double* __restrict__ trial) {
     constexpr int NRED = ENERGY_ONLY ? 1 : 10;
     __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -245,6 +246,16 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
         return t;
     };
     // one member tet: gather, evaluate, add into the lane's partial sums
+    // trial position of the centre vertex (twg_mesh_vertex_trial_energy: the line search of VertexSmoother.cpp:505-541 moves the
+    // vertex, asks getNewEnergy, and moves it back -- here the mesh stays untouched and the ring sees the vertex at `trial`)
+    uint64_t g_cur = 0;
+    auto override_centre = [&](double* x, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int32_t c) {
+        const double tx = __ldg(trial + 3 * g_cur), ty = __ldg(trial + 3 * g_cur + 1), tz = __ldg(trial + 3 * g_cur + 2);
+        const int32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (a[j] == c) { x[3 * j] = tx; x[3 * j + 1] = ty; x[3 * j + 2] = tz; }
+    };
     auto member = [&](int4 t, int32_t c, double* acc) {
         int32_t a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
         // removed slots (negative first index) and out-of-range ids contribute nothing and are never dereferenced
@@ -265,6 +276,7 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
         gather_vertex(V, a1, x + 3);
         gather_vertex(V, a2, x + 6);
         gather_vertex(V, a3, x + 9);
+        if (trial) override_centre(x, a0, a1, a2, a3, c);
         tw::Amips r;
         tw::amips_eval<!ENERGY_ONLY>(x, r);
         acc[0] += r.E;
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
     uint32_t row_n3 = stage_row(g + 3 * nwarps);
 
     for (; g < nG; g += nwarps) {
+        g_cur = g;
         // ---- issue the loads of the later rings first
         const uint32_t row_n4 = stage_row(g + 4 * nwarps);
         const RingHead h_n3 = stage_head(g + 3 * nwarps, row_n3);
@@ -345,24 +358,26 @@ __global__ void __launch_bounds__(256, 3) amips_ring_kernel(const double* __rest
     }
 }
 
-// amips_ring_kernel with the VERTEX GATHER as a pipeline stage of its own (round 2). In the kernel above a ring's last dependent
-// load -- the 72 B of its members' vertices -- is the one the warp waits for (ncu r01: long_scoreboard 2.8, 0.41 of the HBM
-// peak at 94 B/tet of traffic, i.e. no wasted bytes, only latency). Here every lane hands the twelve coordinates of ITS member
-// of ring i+1 to the asynchronous copy unit (cp.async, 8 B each -- a vertex is only 8-byte aligned) before it evaluates its
-// member of ring i from shared memory: the gather is in flight during ~150 FP64 instructions and needs no registers.
-// Stages per iteration: row(i+5), CSR bounds(i+4), member ids(i+3), tet records(i+2), vertices(i+1) -> shared memory, evaluate(i).
-// Shared memory: 2 stages x 12 coordinates x 32 lanes x 8 B = 6 KiB per warp, component-major (conflict-free 64-bit reads).
+// amips_ring_kernel with the VERTEX GATHER announced one ring ahead (round 2). In the kernel above a ring's last dependent
+// load -- the 72 B of its members' vertices -- is the one the warp waits for (ncu r01: long_scoreboard 2.8, 0.41 of the HBM peak
+// at 94 B/tet of traffic: no wasted bytes, only latency). Here the tet records arrive one iteration earlier (one more
+// pipeline stage) and every lane PREFETCHES the vertices of its member of ring i+1 into L2 (prefetch.global.L2: no register,
+// no shared memory) before it gathers and evaluates its member of ring i, whose lines then come from L2 instead of HBM.
+// Stages per iteration: row(i+5), CSR bounds(i+4), member ids(i+3), tet records(i+2), vertex prefetch(i+1), gather + evaluate(i).
+// Measured and NOT kept (r2s6): staging the vertices in shared memory with cp.async (8 B per copy, a vertex is only 8-byte
+// aligned): 11.7 instead of 28.0 G tets/s, long_scoreboard 13.9 -- 384 LDGSTS per warp and ring cost more than they hide.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <bool ENERGY_ONLY>
-__global__ void __launch_bounds__(256, 3) amips_ring_async_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
-                                                                  const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
-                                                                  const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
-                                                                  double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
-                                                                  uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg) {
+__global__ void __launch_bounds__(256, 3) amips_ring_pf_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
+                                                               const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
+                                                               const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
+                                                               double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
+                                                               uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg,
+                                                               const double* __restrict__ trial) {
     constexpr int NRED = ENERGY_ONLY ? 1 : 10;
-    extern __shared__ __align__(16) double dyn[];                       // [8 warps][2 stages][12][32]
     __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* vb = dyn + (size_t)wib * 2 * 12 * 32;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     const uint64_t gl = nG - 1;  // prefetches past the end re-read the last ring (valid addresses, never consumed)
@@ -388,41 +403,48 @@ __global__ void __launch_bounds__(256, 3) amips_ring_async_kernel(const double* 
         if (k < h.cnt && (uint64_t)ti < nT) t = __ldg(tets + ti);
         return t;
     };
-    // centre to slot 0 (:640-651); getNewEnergy keeps the stored order. Returns false for a tet that must not be dereferenced.
-    auto rotate = [&](int4 t, int32_t c, int32_t* a) -> bool {
+    // stage "vertex prefetch": the lane's member of a later ring -> L2 (first and last double of every vertex: a 24-byte vertex
+    // may straddle two lines)
+    auto stage_prefetch = [&](const RingHead& h, int4 t) {
+        if ((uint32_t)lane < h.cnt && (uint32_t)t.x < nV && (uint32_t)t.y < nV && (uint32_t)t.z < nV && (uint32_t)t.w < nV) {
+            const int32_t a[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const double* src = V + 3 * (size_t)a[v];
+                prefetch_l2(src);
+                prefetch_l2(src + 2);
+            }
+        }
+    };
+    // trial position of the centre vertex (twg_mesh_vertex_trial_energy: the line search of VertexSmoother.cpp:505-541 moves the
+    // vertex, asks getNewEnergy, and moves it back -- here the mesh stays untouched and the ring sees the vertex at `trial`)
+    uint64_t g_cur = 0;
+    auto override_centre = [&](double* x, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int32_t c) {
+        const double tx = __ldg(trial + 3 * g_cur), ty = __ldg(trial + 3 * g_cur + 1), tz = __ldg(trial + 3 * g_cur + 2);
+        const int32_t a[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (a[j] == c) { x[3 * j] = tx; x[3 * j + 1] = ty; x[3 * j + 2] = tz; }
+    };
+    auto member = [&](int4 t, int32_t c, double* acc) {
         int32_t a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
-        if ((uint32_t)a0 >= nV || (uint32_t)a1 >= nV || (uint32_t)a2 >= nV || (uint32_t)a3 >= nV) return false;
-        if (!ENERGY_ONLY) {
+        // removed slots (negative first index) and out-of-range ids contribute nothing and are never dereferenced
+        if ((uint32_t)a0 >= nV || (uint32_t)a1 >= nV || (uint32_t)a2 >= nV || (uint32_t)a3 >= nV) {
+            atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
+            return;
+        }
+        if (!ENERGY_ONLY) {  // :640-651, centre to slot 0
             const int start = (a0 == c) ? 0 : (a1 == c) ? 1 : (a2 == c) ? 2 : (a3 == c) ? 3 : 0;
             const bool r1 = (start & 1) != 0, r2 = (start & 2) != 0;
             const int32_t b0 = r1 ? a1 : a0, b1 = r1 ? a2 : a1, b2 = r1 ? a3 : a2, b3 = r1 ? a0 : a3;
             a0 = r2 ? b2 : b0; a1 = r2 ? b3 : b1; a2 = r2 ? b0 : b2; a3 = r2 ? b1 : b3;
         }
-        a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
-        return true;
-    };
-    // stage "vertices": the lane's member of ring h -> shared-memory stage st (one commit group per ring, empty or not)
-    auto stage_verts = [&](const RingHead& h, int4 t, int st) -> bool {
-        bool okm = false;
-        if ((uint32_t)lane < h.cnt) {
-            int32_t a[4];
-            okm = rotate(t, h.c, a);
-            if (okm) {
-                double* dst = vb + (size_t)st * 12 * 32 + lane;
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const double* src = V + 3 * (size_t)a[v];
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) cp_async8(dst + (3 * v + k) * 32, src + k);
-                }
-            } else {
-                atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
-            }
-        }
-        cp_async_commit();
-        return okm;
-    };
-    auto accumulate = [&](const double* x, double* acc) {
+        double x[12];
+        gather_vertex(V, a0, x);
+        gather_vertex(V, a1, x + 3);
+        gather_vertex(V, a2, x + 6);
+        gather_vertex(V, a3, x + 9);
+        if (trial) override_centre(x, a0, a1, a2, a3, c);
         tw::Amips r;
         tw::amips_eval<!ENERGY_ONLY>(x, r);
         acc[0] += r.E;
@@ -443,42 +465,22 @@ __global__ void __launch_bounds__(256, 3) amips_ring_async_kernel(const double* 
     uint32_t ti_n2 = stage_tid(h_n2, lane);
     RingHead h_n3 = stage_head(g + 3 * nwarps, stage_row(g + 3 * nwarps));
     uint32_t row_n4 = stage_row(g + 4 * nwarps);
-    int st = 0;
-    bool ok_cur = stage_verts(h_cur, tet_cur, st);   // ring g -> stage 0
 
     for (; g < nG; g += nwarps) {
+        g_cur = g;
         // ---- issue the loads of the later rings first
         const uint32_t row_n5 = stage_row(g + 5 * nwarps);
         const RingHead h_n4 = stage_head(g + 4 * nwarps, row_n4);
         const uint32_t ti_n3 = stage_tid(h_n3, lane);
         const int4 tet_n2 = stage_tet(h_n2, lane, ti_n2);
-        const bool ok_n1 = stage_verts(h_n1, tet_n1, st ^ 1);   // vertices of ring g+1 -> the other stage
-        // ---- ring g: its vertices were requested one iteration ago
-        cp_async_wait<1>();
-        __syncwarp();
+        stage_prefetch(h_n1, tet_n1);
+        // ---- ring g
         double acc[NRED];
 #pragma unroll
         for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-        if ((uint32_t)lane < h_cur.cnt && ok_cur) {
-            double x[12];
-            const double* srcv = vb + (size_t)st * 12 * 32 + lane;
-#pragma unroll
-            for (int k = 0; k < 12; ++k) x[k] = srcv[k * 32];
-            accumulate(x, acc);
-        }
-        for (uint32_t k = 32 + lane; k < h_cur.cnt; k += 32) {  // rings of more than 32 tets: the rest is fetched on demand
-            const int4 t = stage_tet(h_cur, k, stage_tid(h_cur, k));
-            int32_t a[4];
-            if (rotate(t, h_cur.c, a)) {
-                double x[12];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) gather_vertex(V, a[v], x + 3 * v);
-                accumulate(x, acc);
-            } else {
-                atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
-            }
-        }
-        __syncwarp();  // every lane has read stage `st` before the next iteration refills it
+        if ((uint32_t)lane < h_cur.cnt) member(tet_cur, h_cur.c, acc);
+        for (uint32_t k = 32 + lane; k < h_cur.cnt; k += 32)  // rings of more than 32 tets: the rest is fetched on demand
+            member(stage_tet(h_cur, k, stage_tid(h_cur, k)), h_cur.c, acc);
         if (ENERGY_ONLY) {
             double en = warp_sum(acc[0]);
             if (lane == 0) {  // getNewEnergy :619-622
@@ -518,17 +520,13 @@ __global__ void __launch_bounds__(256, 3) amips_ring_async_kernel(const double* 
             }
         }
         // ---- advance the pipeline
-        h_cur = h_n1; ok_cur = ok_n1;
+        h_cur = h_n1; tet_cur = tet_n1;
         h_n1 = h_n2; tet_n1 = tet_n2;
         h_n2 = h_n3; ti_n2 = ti_n3;
         h_n3 = h_n4;
         row_n4 = row_n5;
-        st ^= 1;
     }
-    cp_async_wait<0>();
 }
-
-constexpr size_t kRingAsyncSmem = (size_t)8 * 2 * 12 * 32 * sizeof(double);  // 48 KiB of staged vertices per CTA
 
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
 
@@ -589,19 +587,20 @@ int ring_waves(const twg_ctx* c) { return c->opt.ring_waves; }
 
 template <bool ENERGY_ONLY>
 int launch_ring(twg_ctx* c, cudaStream_t st, const double* dV, uint32_t nV, const int4* dTets, uint64_t nT, const int32_t* dTids, const uint64_t* dOff,
-                const int32_t* dCenter, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk) {
-    if (c->opt.ring_async) {
-        static bool attr_set[64] = {false};  // per device: the 48 KiB of dynamic shared memory need the opt-in once
-        if (c->device < 64 && !attr_set[c->device]) {
-            TWG_CUDA(c, cudaFuncSetAttribute(amips_ring_async_kernel<ENERGY_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingAsyncSmem));
-            attr_set[c->device] = true;
-        }
-        TWG_LAUNCH(c, (amips_ring_async_kernel<ENERGY_ONLY>), grid_for(c, nG, 8, ring_waves(c)), 256, kRingAsyncSmem, st, dV, dTets, dTids, dOff, dCenter, dVids, nG,
-                   dE, dJ3, dH9, dOk, nV, nT, c->dcounters);
+                const int32_t* dCenter, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk,
+                const double* dTrial = nullptr) {
+    if (c->opt.ring_prefetch) {
+        TWG_LAUNCH(c, (amips_ring_pf_kernel<ENERGY_ONLY>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids, nG, dE, dJ3, dH9,
+                   dOk, nV, nT, c->dcounters, dTrial);
         return 0;
     }
-    TWG_LAUNCH(c, (amips_ring_kernel<ENERGY_ONLY>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids, nG, dE, dJ3, dH9, dOk, nV,
-               nT, c->dcounters);
+    if (c->opt.ring_minb >= 4) {  // 64 registers, 32 warps per SM
+        TWG_LAUNCH(c, (amips_ring_kernel<ENERGY_ONLY, 4>), grid_for(c, nG, 8, ring_waves(c) > 4 ? ring_waves(c) : 4), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids,
+                   nG, dE, dJ3, dH9, dOk, nV, nT, c->dcounters, dTrial);
+        return 0;
+    }
+    TWG_LAUNCH(c, (amips_ring_kernel<ENERGY_ONLY, 3>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids, nG, dE, dJ3, dH9, dOk,
+               nV, nT, c->dcounters, dTrial);
     return 0;
 }
 
@@ -654,6 +653,18 @@ int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, con
     TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
     return launch_ring<false>(c, pick(c, stream), dV, nV, (const int4*)dTets, nT, dAdjTets, dAdjOff, (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk);
+}
+
+// getNewEnergy of the one-ring of vertex dVids[g] with that vertex at dTrial[3g..3g+2] (the mesh itself is not modified)
+int twg_amips_vertex_trial_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets,
+                                      const uint64_t* dAdjOff, const int32_t* dVids, const double* dTrial, uint64_t nG, double* dE, void* stream) {
+    TWG_CHECK(c, c && dV && dTets && dAdjTets && dAdjOff && dVids && dTrial && dE, TWG_ERR_INVALID_ARG, "null argument");
+    TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
+    TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
+    if (nG == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    return launch_ring<true>(c, pick(c, stream), dV, nV, (const int4*)dTets, nT, dAdjTets, dAdjOff, (const int32_t*)nullptr, dVids, nG, dE, (double*)nullptr,
+                             (double*)nullptr, (uint8_t*)nullptr, dTrial);
 }
 
 int twg_amips_ring_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dTids,

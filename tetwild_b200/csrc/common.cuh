@@ -22,18 +22,21 @@ struct twg_options {
     int env_top = 64;          // pair records staged in shared memory
     int env_bound = 1;         // oriented facet bound before the exact leaf routine
     int envelope_sort = 1;     // Morton-order large batches before traversal
-    int sort_bits = 24;        // Morton bits that are sorted
+    int surface_order = 1;     // facet order of the envelope structure: 1 Hilbert curve, 0 Z (Morton) curve
+    int sort_bits = 24;        // key bits that are sorted
+    int sort_curve = 0;        // query order: 0 Z (Morton) curve, 1 Hilbert curve
     long long chunk_points = 1ll << 20;  // points per staging chunk of the host entry points
     int ring_waves = 3;        // resident CTAs per SM of the one-ring kernels
-    int ring_async = 1;        // one-ring kernels gather the vertices of the next ring with cp.async into shared memory
+    int ring_prefetch = 0;     // one-ring kernels prefetch the vertices of the next ring into L2 (measured slower: 17 vs 28 G tets/s)
+    int ring_minb = 3;         // resident CTAs per SM the one-ring kernel's registers are capped for (3: 80 registers, 4: 64)
     int winding_minb = 3;
     int winding_sort = 1;
     int winding_leaf = 64;
     int winding_device_build = 1;
     int amips_tma = 1;
-    int nearest_mode = 1;      // 1: round-scheduled lanes, 2: packets + one query per warp, 0: per-lane descents (round 1)
+    int nearest_mode = 1;      // 1: packets of 32 queries (+ one query per warp past the budget), 2: round-scheduled lanes, 0: per-lane descents (round 1)
     int nearest_group = 64;    // queries per claimed group of the round-scheduled nearest kernel
-    int nearest_budget = 96;   // node visits a packet of 32 queries may spend before its queries are finished one per warp
+    int nearest_budget = 1 << 30;  // node visits a packet of 32 queries may spend before its queries are finished one per warp (measured: never pays)
     int trace = 0;
 };
 

@@ -1217,14 +1217,14 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     const bool sorted = n >= TWG_SORT_MIN && c->opt.envelope_sort;
     if (sorted) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box, &Pq));
     TWG_CUDA(c, cudaMemsetAsync(lane->counters, 0, sizeof(unsigned long long), st));
-    if (sorted && c->opt.nearest_mode == 1 && s->nLeafP >= 8) {  // round-scheduled lanes (form 3)
+    if (sorted && c->opt.nearest_mode == 2 && s->nLeafP >= 8) {  // round-scheduled lanes (form 3)
         const int group = c->opt.nearest_group;
         const unsigned grid = grid_persistent(c, (n + group - 1) / group, kEnvThreads / 32, 6);
         TWG_LAUNCH(c, (nearest_rounds_kernel<6>), grid, kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, dFacet, dNearest, dD2, lane->counters, group,
                    c->opt.env_quorum, c->opt.trace ? c->dcounters : (unsigned long long*)nullptr);
         return twg_lane_mark(c, lane);
     }
-    if (sorted && c->opt.nearest_mode == 2 && s->nLeafP >= 8) {  // packets of 32 neighbouring queries share one traversal
+    if (sorted && c->opt.nearest_mode == 1 && s->nLeafP >= 8) {  // packets of 32 neighbouring queries share one traversal (default)
         const uint64_t claims = ((n + 31) / 32 + kPacketChunk - 1) / kPacketChunk;
         TWG_LAUNCH(c, nearest_packet_kernel, grid_persistent(c, claims, kEnvThreads / 32, 6), kEnvThreads, top_smem(s), st, view_of(s), Pq, perm, n, dFacet,
                    dNearest, dD2, lane->counters, c->opt.nearest_budget);

@@ -18,6 +18,9 @@ extern "C" int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint3
                                              const uint64_t* dAdjOff, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3,
                                              double* dH9, uint8_t* dOk, void* stream);
 
+extern "C" int twg_amips_vertex_trial_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets,
+                                                 const uint64_t* dAdjOff, const int32_t* dVids, const double* dTrial, uint64_t nG, double* dE, void* stream);
+
 struct twg_mesh {
     twg_ctx* ctx = nullptr;
     uint32_t nV = 0, capV = 0;
@@ -497,6 +500,50 @@ int twg_mesh_ring_energy(twg_mesh* m, const int32_t* t_ids, const uint64_t* grou
     TWG_CUDA(c, cudaMemcpyAsync(E, dE, nG * 8, cudaMemcpyDeviceToHost, st));
     TWG_CUDA(c, cudaStreamSynchronize(st));
     return 0;
+}
+
+// The line search of the smoother (VertexSmoother.cpp:505-541): "move v to p, getNewEnergy(conn_tets[v]), move it back" for n
+// (vertex, trial position) pairs at once. The resident mesh is NOT modified: every ring is evaluated with its centre vertex at
+// the trial position, so the pairs are independent -- all step sizes of one Newton step, or the steps of many candidates.
+int twg_mesh_vertex_trial_energy(twg_mesh* m, const int32_t* v_ids, const double* xyz, uint64_t n, double* E) {
+    twg_ctx* c = m ? m->ctx : nullptr;
+    TWG_CHECK(c, m && (n == 0 || (v_ids && xyz && E)), TWG_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return 0;
+    for (uint64_t i = 0; i < n; ++i) TWG_CHECK(c, v_ids[i] >= 0 && (uint32_t)v_ids[i] < m->nV, TWG_ERR_INVALID_ARG, "vertex id out of range");
+    TWG_TRY(twg_mesh_build_rings(m));
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    const size_t ib = up256(n * 4), xb = up256(n * 24), eb = up256(n * 8);
+    TWG_TRY(twg_ensure_scratch(c, 0, ib + xb + eb));
+    char* d = (char*)c->dscratch[0];
+    if (n <= kSmallCall) {  // one packed copy each way through the pinned slabs
+        TWG_TRY(twg_ensure_pinned(c, ib + xb, eb));
+        memcpy(c->pin_in[0], v_ids, n * 4);
+        memcpy((char*)c->pin_in[0] + ib, xyz, n * 24);
+        TWG_CUDA(c, cudaMemcpyAsync(d, c->pin_in[0], ib + n * 24, cudaMemcpyHostToDevice, st));
+    } else {
+        TWG_CUDA(c, cudaMemcpyAsync(d, v_ids, n * 4, cudaMemcpyHostToDevice, st));
+        TWG_CUDA(c, cudaMemcpyAsync(d + ib, xyz, n * 24, cudaMemcpyHostToDevice, st));
+    }
+    TWG_TRY(twg_amips_vertex_trial_energy_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, (const int32_t*)d, (const double*)(d + ib), n,
+                                              (double*)(d + ib + xb), st));
+    if (n <= kSmallCall) {
+        TWG_CUDA(c, cudaMemcpyAsync(c->pin_out[0], d + ib + xb, n * 8, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+        memcpy(E, c->pin_out[0], n * 8);
+    } else {
+        TWG_CUDA(c, cudaMemcpyAsync(E, d + ib + xb, n * 8, cudaMemcpyDeviceToHost, st));
+        TWG_CUDA(c, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+int twg_mesh_vertex_trial_energy_dev(twg_mesh* m, const int32_t* dVids, const double* dXyz, uint64_t n, double* dE, void* stream) {
+    twg_ctx* c = m ? m->ctx : nullptr;
+    TWG_CHECK(c, m && dVids && dXyz && dE, TWG_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return 0;
+    TWG_TRY(twg_mesh_build_rings(m));
+    return twg_amips_vertex_trial_energy_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, dVids, dXyz, n, dE, stream);
 }
 
 static int per_tet_host(twg_mesh* m, int what, const int32_t* t_ids, uint64_t n, double* out0, double* out1) {

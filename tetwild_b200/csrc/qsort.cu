@@ -66,6 +66,26 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
     v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
+// 30-bit Hilbert index of a point on a 1024^3 grid (Skilling's transpose form, as in surface.cu): consecutive indices are
+// adjacent cells, so a run of sorted queries is a connected blob without the jumps of the Z order (option sort_curve)
+__device__ __forceinline__ uint32_t hilbert30(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << 9;
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+    return (spread10(X[0] ^ t) << 2) | (spread10(X[1] ^ t) << 1) | spread10(X[2] ^ t);
+}
 struct Box6 {
     double v[6];  // lo xyz, hi xyz
 };
@@ -81,7 +101,7 @@ __device__ __forceinline__ uint32_t tile_elem(int w, int r, int l) { return (uin
 
 // Morton keys of the points + histogram of the first digit of every tile: hist[d * ntiles + tile]
 __global__ void __launch_bounds__(kSortThreads) qs_keys_hist_kernel(const double* __restrict__ Q, uint64_t n, const unsigned long long* __restrict__ bounds, Box6 known,
-                                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint32_t ntiles, Digit dg) {
+                                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ hist, uint32_t ntiles, Digit dg, int hilbert) {
     __shared__ uint32_t h[256];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -99,14 +119,16 @@ __global__ void __launch_bounds__(kSortThreads) qs_keys_hist_kernel(const double
     for (int r = 0; r < kSortItems; ++r) {
         const uint64_t i = base + tile_elem(w, r, l);
         if (i < n) {
-            uint32_t code = 0;
+            uint32_t code = 0, qd[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 const double x = __ldg(Q + 3 * i + c);
                 double u = isfinite(x) ? (x - lo[c]) * inv[c] : 0.0;
                 u = fmin(fmax(u, 0.0), 1.0);
-                code |= spread10((uint32_t)(u * 1023.0)) << c;
+                qd[c] = (uint32_t)(u * 1023.0);
+                code |= spread10(qd[c]) << c;
             }
+            if (hilbert) code = hilbert30(qd[0], qd[1], qd[2]);
             keys[i] = code;
             atomicAdd(&h[dg.of(code)], 1u);
         }
@@ -313,7 +335,7 @@ int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* d
         const int width = (bits - 8 * p) < 8 ? (bits - 8 * p) : 8;
         dg.mask = (1u << width) - 1u;
         if (p == 0)
-            TWG_LAUNCH(c, qs_keys_hist_kernel, ntiles, kSortThreads, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, kbuf[0], hist, ntiles, dg);
+            TWG_LAUNCH(c, qs_keys_hist_kernel, ntiles, kSortThreads, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, kbuf[0], hist, ntiles, dg, c->opt.sort_curve);
         else
             TWG_LAUNCH(c, qs_tile_hist_kernel, ntiles, kSortThreads, 0, st, (const uint32_t*)kbuf[cur], n, hist, ntiles, dg);
         TWG_LAUNCH(c, qs_row_scan_kernel, 256, 256, 0, st, hist, ntiles, total);

@@ -65,11 +65,40 @@ __device__ __forceinline__ unsigned long long spread3(unsigned long long v) {
     return v;
 }
 
+// Hilbert index of a point on a 2^21 grid (J. Skilling, "Programming the Hilbert curve", 2004: Gray-code untangling of the
+// transposed axes, then bit interleaving). Facets are ordered along the Hilbert curve rather than the Z curve: every range of
+// consecutive facets -- and every node of the implicit heap is one -- is then a CONNECTED piece of the curve, without the long
+// jumps of the Z order, so sibling boxes overlap less and a query enters fewer subtrees (option surface_order: 1 Hilbert, 0 Morton).
+__device__ __forceinline__ unsigned long long hilbert63(uint32_t x, uint32_t y, uint32_t z) {
+    uint32_t X[3] = {x, y, z};
+    const uint32_t M = 1u << 20;
+    // inverse undo excess work
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+    // Gray encode
+    X[1] ^= X[0];
+    X[2] ^= X[1];
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[2] & Q) t ^= Q - 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) X[i] ^= t;
+    // interleave: bit b of X[0] is the most significant of the three bits of level b
+    return (spread3(X[0]) << 2) | (spread3(X[1]) << 1) | spread3(X[2]);
+}
+
 __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ V, const uint32_t* __restrict__ F, uint32_t nF,
-                                                     const unsigned long long* __restrict__ bounds, unsigned long long* keys, uint32_t* vals) {
+                                                     const unsigned long long* __restrict__ bounds, unsigned long long* keys, uint32_t* vals, int hilbert) {
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nF) return;
     unsigned long long code = 0;
+    uint32_t qd[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         const double lo = dec(bounds[c]), hi = dec(bounds[3 + c]);
@@ -77,9 +106,10 @@ __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ 
         const double ext = hi - lo;
         double u = ext > 0.0 ? (ctr - lo) / ext : 0.0;
         u = fmin(fmax(u, 0.0), 1.0);
-        code |= spread3((unsigned long long)(u * 2097151.0)) << c;
+        qd[c] = (uint32_t)(u * 2097151.0);
+        code |= spread3((unsigned long long)qd[c]) << c;
     }
-    keys[f] = code;
+    keys[f] = hilbert ? hilbert63(qd[0], qd[1], qd[2]) : code;
     vals[f] = f;
 }
 
@@ -174,7 +204,7 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
         B_CUDA(cudaMemcpyAsync(&bad, bounds + 6, sizeof(bad), cudaMemcpyDeviceToHost, st));
         B_CUDA(cudaStreamSynchronize(st));
         if (bad != 0) return fail(twg_fail(c, TWG_ERR_INVALID_ARG, "facet references a vertex out of range", __FILE__, __LINE__));
-        morton_kernel<<<(nF + 255) / 256, 256, 0, st>>>(dV, dF, nF, bounds, keys, vals);
+        morton_kernel<<<(nF + 255) / 256, 256, 0, st>>>(dV, dF, nF, bounds, keys, vals, c->opt.surface_order);
         c->launches++;
     }
     static_assert(sizeof(int) == 4, "cub takes int item counts; nF < 2^31 is checked by the callers");
