@@ -14,12 +14,16 @@ def main():
     torch.cuda.set_stream(torch.cuda.Stream())
     s = torch.cuda.current_stream().cuda_stream
     if part in ("envelope", "faces", "nearest"):
-        V, F = synth.torus_knot(1000, 100)
+        if part == "faces":   # the bench's envelope_faces workload: icosphere, faces of edge ~ diag/50
+            V, F = synth.icosphere(5)
+            V = synth.normalise_unit_diag(V)
+        else:
+            V, F = synth.torus_knot(1000, 100)
         S = tw.Surface(ctx, V, F)
         sd, eps, eps2 = synth.state_eps(1e-3)
         if part == "faces":
-            n = n or 20000
-            T = torch.from_numpy(synth.face_queries(V, F, n, 0.05, eps)).cuda()
+            n = n or 100000
+            T = torch.from_numpy(synth.face_queries(V, F, n, 0.02, eps, seed=3)).cuda()
             O = torch.empty(n, device="cuda", dtype=torch.uint8)
             fn = lambda: S.faces_out_dev(T.data_ptr(), n, sd, eps2, O.data_ptr(), s)
         else:
@@ -51,6 +55,14 @@ def main():
         E = torch.empty(nG, device="cuda", dtype=torch.float64); J = torch.empty(nG, 3, device="cuda", dtype=torch.float64); H = torch.empty(nG, 9, device="cuda", dtype=torch.float64)
         K = torch.empty(nG, device="cuda", dtype=torch.uint8)
         fn = lambda: ctx.amips_ring_ejh_dev(dV.data_ptr(), dV.shape[0], dT4.data_ptr(), n, 0, dOff.data_ptr(), dCen.data_ptr(), nG, E.data_ptr(), J.data_ptr(), H.data_ptr(), K.data_ptr(), s)
+    elif part == "quality":   # the bench's amips_quality workload: C3 indexed layout on the resident mesh
+        import bench
+        n = n or 15_000_000
+        dV, dT4, dOff, dCen = bench.rings_on_device(n, 7, torch.device("cuda", 0))
+        M = tw.TetMesh(ctx, dV.cpu().numpy(), dT4.cpu().numpy())
+        del dV, dT4
+        q = torch.empty(n, device="cuda", dtype=torch.float64)
+        fn = lambda: M.quality_dev(0, n, q.data_ptr(), s)
     elif part == "mesh":
         # resident tet mesh: whole-mesh quality + dihedral passes and one-ring Newton terms for every vertex
         g = n or 150

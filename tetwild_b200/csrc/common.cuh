@@ -37,6 +37,7 @@ struct twg_options {
     int nearest_mode = 1;      // 1: packets of 32 queries (+ one query per warp past the budget), 2: round-scheduled lanes, 0: per-lane descents (round 1)
     int nearest_group = 64;    // queries per claimed group of the round-scheduled nearest kernel
     int nearest_budget = 1 << 30;  // node visits a packet of 32 queries may spend before its queries are finished one per warp (measured: never pays)
+    int fast_calls = 1;        // tiny host calls go through the zero-copy slab (twg_fast_*)
     int trace = 0;
 };
 
@@ -68,6 +69,11 @@ struct twg_ctx {
     // device scratch, grown on demand
     void* dscratch[TWG_NUM_STREAMS] = {nullptr, nullptr, nullptr};
     size_t dscratch_bytes[TWG_NUM_STREAMS] = {0, 0, 0};
+    // zero-copy slab for tiny calls (twg_fast_*): mapped pinned host memory the kernels read and write directly, plus the
+    // completion word the host spins on -- no cudaMemcpy, no cudaStreamSynchronize on the latency path
+    void* fast_slab = nullptr;
+    size_t fast_bytes = 0;
+    uint32_t fast_seq = 0;
     std::vector<twg_lane> lanes;
     uint64_t lane_tick = 0;
     unsigned long long* dcounters = nullptr;  // device, TWG_NUM_DEBUG_COUNTERS slots (twg_debug_counter)
@@ -116,6 +122,12 @@ inline int twg_fail(const twg_ctx* c, int code, const char* what, const char* fi
     } while (0)
 
 int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
+// Tiny calls (the un-batched call sites of the sequential scheduler: one face, one point, one one-ring): the arguments are
+// written into a mapped pinned slab that the kernel reads over PCIe, the results are written by the kernel straight into the
+// same slab, and completion is a word in that slab written by a one-warp kernel queued behind the work; the host spins on it.
+// twg_fast_slab returns the slab (host pointer == device pointer under unified addressing), at least `bytes` long.
+int twg_fast_slab(twg_ctx* c, size_t bytes, char** slab);
+int twg_fast_wait(twg_ctx* c, cudaStream_t st);
 int twg_ensure_pinned(twg_ctx* c, size_t in_bytes, size_t out_bytes);
 #define TWG_SORT_MIN 4096  /* batches below this are traversed in the caller's order */
 // the lane of stream `st` (created on first use); *out stays valid until the next twg_get_lane call on this context

@@ -35,6 +35,7 @@ const OptDesc kOpts[] = {
     {"nearest_mode", &twg_options::nearest_mode, nullptr, 0, 2},
     {"nearest_group", &twg_options::nearest_group, nullptr, 32, 4096},
     {"nearest_budget", &twg_options::nearest_budget, nullptr, 1, 1 << 30},
+    {"fast_calls", &twg_options::fast_calls, nullptr, 0, 1},
     {"trace", &twg_options::trace, nullptr, 0, 1},
 };
 
@@ -139,6 +140,7 @@ void twg_destroy(twg_ctx* c) {
         if (c->dscratch[i]) cudaFree(c->dscratch[i]);
     }
     if (c->dcounters) cudaFree(c->dcounters);
+    if (c->fast_slab) cudaFreeHost(c->fast_slab);
     delete c;
 }
 
@@ -232,7 +234,59 @@ int twg_get_lane(twg_ctx* c, cudaStream_t st, twg_lane** out) {
 }
 
 int twg_lane_mark(twg_ctx* c, twg_lane* lane) {
+    // only caller-stream lanes are ever recycled; the context's own streams are synchronised by the host entry points
+    if (lane >= c->lanes.data() && lane < c->lanes.data() + TWG_NUM_STREAMS) return 0;
     TWG_CUDA(c, cudaEventRecord(lane->done, lane->stream));
+    return 0;
+}
+
+namespace {
+__global__ void fast_signal_kernel(volatile uint32_t* flag, uint32_t seq) {
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *flag = seq;
+    }
+}
+}  // namespace
+
+int twg_fast_slab(twg_ctx* c, size_t bytes, char** slab) {
+    const size_t need = bytes + 256;  // the first 256 bytes hold the completion word
+    if (c->fast_bytes < need) {
+        if (c->fast_slab) {
+            TWG_CUDA(c, cudaStreamSynchronize(c->streams[0]));
+            TWG_CUDA(c, cudaFreeHost(c->fast_slab));
+            c->fast_slab = nullptr;
+            c->fast_bytes = 0;
+        }
+        const size_t want = need < (1u << 16) ? (1u << 16) : need * 2;
+        TWG_CUDA(c, cudaHostAlloc(&c->fast_slab, want, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(c->fast_slab, 0, 256);
+        c->fast_bytes = want;
+    }
+    *slab = (char*)c->fast_slab + 256;
+    return 0;
+}
+
+int twg_fast_wait(twg_ctx* c, cudaStream_t st) {
+    volatile uint32_t* flag = (volatile uint32_t*)c->fast_slab;
+    const uint32_t seq = ++c->fast_seq ? c->fast_seq : ++c->fast_seq;  // never 0
+    fast_signal_kernel<<<1, 32, 0, st>>>(flag, seq);
+    c->launches++;
+    TWG_CUDA(c, cudaGetLastError());
+    // spin: the word arrives over PCIe right after the results (posted writes of one device stay in order)
+    for (unsigned long long spins = 0; *flag != seq; ++spins) {
+        if ((spins & 0xfffff) == 0xfffff) {  // ~ every few ms: has the stream failed?
+            const cudaError_t e = cudaStreamQuery(st);
+            if (e != cudaSuccess && e != cudaErrorNotReady) return twg_fail(c, (int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+            if (e == cudaSuccess && *flag != seq) {  // finished, word not seen yet: one proper synchronize settles it
+                TWG_CUDA(c, cudaStreamSynchronize(st));
+                break;
+            }
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
     return 0;
 }
 

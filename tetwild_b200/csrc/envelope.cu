@@ -1274,6 +1274,27 @@ static int points_host(twg_surface* s, int what, const double* P, uint64_t n, do
     const uint64_t cmax = n < chunk ? n : chunk;
     const size_t pb = up(cmax * 24), ob = up(cmax), fb = up(cmax * 4), nb = up(cmax * 24), db = up(cmax * 8);
     for (int k = 0; k < TWG_NUM_STREAMS; ++k) TWG_TRY(twg_ensure_scratch(c, k, pb + ob + fb + nb + db));
+    if (n <= 64 && c->opt.fast_calls) {
+        // ONE point of the sequential scheduler (EdgeCollapser.cpp:312,322; VertexSmoother.cpp:358): the query and the answer live in
+        // the mapped slab, the kernel reads and writes them over PCIe, the host spins on the completion word
+        char* slab;
+        const size_t qb = up(n * 24), rb = up(n), fb2 = up(n * 4), nb2 = up(n * 24), db2 = up(n * 8);
+        TWG_TRY(twg_fast_slab(c, qb + rb + fb2 + nb2 + db2, &slab));
+        cudaStream_t st = c->streams[0];
+        memcpy(slab, P, n * 24);
+        if (what == 0) {
+            TWG_TRY(twg_envelope_points_out_dev(s, (const double*)slab, n, eps2, (uint8_t*)(slab + qb), st));
+        } else {
+            TWG_TRY(twg_nearest_dev(s, (const double*)slab, n, facet ? (uint32_t*)(slab + qb + rb) : nullptr, nearest ? (double*)(slab + qb + rb + fb2) : nullptr,
+                                    d2 ? (double*)(slab + qb + rb + fb2 + nb2) : nullptr, st));
+        }
+        TWG_TRY(twg_fast_wait(c, st));
+        if (what == 0) memcpy(out, slab + qb, n);
+        if (facet) memcpy(facet, slab + qb + rb, n * 4);
+        if (nearest) memcpy(nearest, slab + qb + rb + fb2, n * 24);
+        if (d2) memcpy(d2, slab + qb + rb + fb2 + nb2, n * 8);
+        return 0;
+    }
     if (what == 0 && n <= 16384) {  // a few points (EdgeCollapser.cpp:322 asks for one): pinned slabs, one copy each way
         TWG_TRY(twg_ensure_pinned(c, up(n * 24), up(n)));
         cudaStream_t st = c->streams[0];
@@ -1342,6 +1363,16 @@ int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, do
     }
     TWG_CUDA(c, cudaSetDevice(c->device));
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    if (n <= 16 && c->opt.fast_calls) {  // the faces of ONE candidate (EdgeCollapser.cpp:770, VertexSmoother.cpp:425): zero-copy slab
+        char* slab;
+        TWG_TRY(twg_fast_slab(c, up(n * 72) + up(n), &slab));
+        cudaStream_t st = c->streams[0];
+        memcpy(slab, tris, n * 72);
+        TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)slab, n, sd, eps2, flags, (uint8_t*)(slab + up(n * 72)), st));
+        TWG_TRY(twg_fast_wait(c, st));
+        memcpy(out, slab + up(n * 72), n);
+        return 0;
+    }
     if (n <= 4096) {  // the faces of one local operation: pinned slabs, one copy each way (pageable copies cost ~10 us each)
         TWG_TRY(twg_ensure_scratch(c, 0, up(n * 72) + up(n)));
         TWG_TRY(twg_ensure_pinned(c, up(n * 72), up(n)));

@@ -186,6 +186,8 @@ unsigned grid_for(twg_ctx* c, uint64_t items, int per_block, int waves) {
 }
 size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 constexpr uint64_t kSmallCall = 8192;  // calls up to this many units take the packed, pinned, one-copy-each-way path
+constexpr uint64_t kFastRings = 32;    // ... and these few go through the zero-copy slab (twg_fast_*): what ONE un-batched call site asks for
+constexpr uint64_t kFastTets = 256;
 
 int grow(twg_mesh* m, uint32_t nV, uint64_t nT) {
     twg_ctx* c = m->ctx;
@@ -394,6 +396,22 @@ int twg_mesh_vertex_ring_ejh(twg_mesh* m, const int32_t* v_ids, uint64_t n, doub
     TWG_TRY(twg_mesh_build_rings(m));
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->streams[0];
+    if (n <= kFastRings && c->opt.fast_calls) {
+        // ONE Newton step of the sequential scheduler: ids and results live in the mapped slab, the kernel reads and writes them over
+        // PCIe, the host spins on the completion word -- one kernel launch is the only driver call that waits on anything
+        char* slab;
+        const size_t ib = up256(n * 4), eb = up256(n * 8), jb = up256(n * 24), hb = up256(n * 72), kb = up256(n);
+        TWG_TRY(twg_fast_slab(c, ib + eb + jb + hb + kb, &slab));
+        memcpy(slab, v_ids, n * 4);
+        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, (const int32_t*)slab, n, (double*)(slab + ib),
+                                              (double*)(slab + ib + eb), (double*)(slab + ib + eb + jb), (uint8_t*)(slab + ib + eb + jb + hb), st));
+        TWG_TRY(twg_fast_wait(c, st));
+        memcpy(E, slab + ib, n * 8);
+        memcpy(J3, slab + ib + eb, n * 24);
+        memcpy(H9, slab + ib + eb + jb, n * 72);
+        if (ok) memcpy(ok, slab + ib + eb + jb + hb, n);
+        return 0;
+    }
     if (n <= kSmallCall) {
         // a handful of rings (what one un-batched Newton step of the scheduler asks for): latency is everything. Ids go
         // through a pinned slab in ONE copy, the four result arrays come back packed in ONE copy (each extra cudaMemcpy of a
@@ -514,6 +532,17 @@ int twg_mesh_vertex_trial_energy(twg_mesh* m, const int32_t* v_ids, const double
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->streams[0];
     const size_t ib = up256(n * 4), xb = up256(n * 24), eb = up256(n * 8);
+    if (n <= kFastRings && c->opt.fast_calls) {  // the step sizes of one line search: zero-copy slab
+        char* slab;
+        TWG_TRY(twg_fast_slab(c, ib + xb + eb, &slab));
+        memcpy(slab, v_ids, n * 4);
+        memcpy(slab + ib, xyz, n * 24);
+        TWG_TRY(twg_amips_vertex_trial_energy_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, (const int32_t*)slab, (const double*)(slab + ib),
+                                                  n, (double*)(slab + ib + xb), st));
+        TWG_TRY(twg_fast_wait(c, st));
+        memcpy(E, slab + ib + xb, n * 8);
+        return 0;
+    }
     TWG_TRY(twg_ensure_scratch(c, 0, ib + xb + eb));
     char* d = (char*)c->dscratch[0];
     if (n <= kSmallCall) {  // one packed copy each way through the pinned slabs
@@ -554,6 +583,18 @@ static int per_tet_host(twg_mesh* m, int what, const int32_t* t_ids, uint64_t n,
         for (uint64_t i = 0; i < n; ++i) TWG_CHECK(c, t_ids[i] >= 0 && (uint64_t)t_ids[i] < m->nT, TWG_ERR_INVALID_ARG, "tet id out of range");
     TWG_CUDA(c, cudaSetDevice(c->device));
     cudaStream_t st = c->streams[0];
+    if (t_ids && n <= kFastTets && c->opt.fast_calls) {  // the tets of one local operation: zero-copy slab, no cudaMemcpy, no synchronize
+        char* slab;
+        const size_t ib = up256(n * 4), eb = up256(n * 8);
+        TWG_TRY(twg_fast_slab(c, ib + 2 * eb, &slab));
+        memcpy(slab, t_ids, n * 4);
+        if (what == 0) TWG_LAUNCH(c, mesh_quality_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, (const int32_t*)slab, n, (double*)(slab + ib));
+        else TWG_LAUNCH(c, mesh_dihedral_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, (const int32_t*)slab, n, (double*)(slab + ib), (double*)(slab + ib + eb));
+        TWG_TRY(twg_fast_wait(c, st));
+        memcpy(out0, slab + ib, n * 8);
+        if (what == 1) memcpy(out1, slab + ib + eb, n * 8);
+        return 0;
+    }
     TWG_TRY(twg_ensure_scratch(c, 0, up256(t_ids ? n * 4 : 0) + 2 * up256(n * 8)));
     size_t o = 0;
     int32_t* dI = nullptr; double *d0, *d1;
