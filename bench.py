@@ -682,20 +682,23 @@ def run_gpu(args, parts):
             ms, kms, launches, win, K, Wm = timed(part, step, pipe.gather, pipe.drain)
             dO = pipe.last()
             if strong:
-                # e2e of the sharded batch: this rank's slice from pinned host memory -> kernel -> NCCL all_gather on the device ->
-                # the whole result back to the host on rank 0 (its own slice elsewhere)
-                hO = pin(torch.empty(n if rank == 0 else m, dtype=torch.uint8))
-                dIn = torch.empty_like(dP)
+                # e2e of the sharded batch: this rank's slice through the host-buffer C-ABI call (pinned host memory in, chunked H2D
+                # overlapped with the kernels, decisions back to the host), then the 1-byte decisions of all ranks gathered over
+                # NVLink (NCCL all_gather of device copies) and the whole result on the host of rank 0
+                hLoc = pin(torch.empty(m, dtype=torch.uint8))
+                hO = pin(torch.empty(n if rank == 0 else 1, dtype=torch.uint8))
                 dLoc = torch.empty(max(shard.shard_sizes(n, world)), device=dev, dtype=torch.uint8)
 
                 def call():
-                    dIn.copy_(hP, non_blocking=True)
-                    S.points_out_dev(dIn.data_ptr(), m, eps2, dLoc.data_ptr(), sh)
-                    full = shard.all_gather_ragged(dLoc[:m], n) if world > 1 else dLoc[:m]
-                    hO.copy_(full if rank == 0 else dLoc[:m], non_blocking=True)
+                    S.points_out(hP.numpy(), eps2, out=hLoc.numpy())
+                    if world > 1:
+                        dLoc[:m].copy_(hLoc, non_blocking=True)
+                        full = shard.all_gather_ragged(dLoc[:m], n)
+                        if rank == 0:
+                            hO.copy_(full, non_blocking=True)
                     torch.cuda.synchronize()
                 e2e_s = e2e_timed(part, call)
-                h2d, d2h = m * 24, int(hO.numel())
+                h2d, d2h = m * 24 + (m if world > 1 else 0), m + (n if (rank == 0 and world > 1) else 0)
             else:
                 hO = pin(torch.empty(n, dtype=torch.uint8))
                 e2e_s = e2e_timed(part, lambda: S.points_out(hP.numpy(), eps2, out=hO.numpy()))
@@ -936,19 +939,21 @@ def run_gpu(args, parts):
             hQ = pin(torch.empty((m, 3), dtype=torch.float64))
             hQ.copy_(dQ)
             if strong:
-                hK = pin(torch.empty(n if rank == 0 else m, dtype=torch.uint8))
-                dIn = torch.empty_like(dQ)
+                hLoc = pin(torch.empty(m, dtype=torch.uint8))
+                hK = pin(torch.empty(n if rank == 0 else 1, dtype=torch.uint8))
                 dLoc = torch.empty(max(shard.shard_sizes(n, world)), device=dev, dtype=torch.uint8)
 
-                def call():
-                    dIn.copy_(hQ, non_blocking=True)
-                    Wt.eval_dev(dIn.data_ptr(), m, 0, dLoc.data_ptr(), sh)
-                    full = shard.all_gather_ragged(dLoc[:m], n) if world > 1 else dLoc[:m]
-                    hK.copy_(full if rank == 0 else dLoc[:m], non_blocking=True)
+                def call():   # host-buffer call on this rank's slice, then the decisions of all ranks gathered over NVLink, whole result on rank 0's host
+                    Wt.eval(hQ.numpy(), want_w=False, out=(None, hLoc.numpy()))
+                    if world > 1:
+                        dLoc[:m].copy_(hLoc, non_blocking=True)
+                        full = shard.all_gather_ragged(dLoc[:m], n)
+                        if rank == 0:
+                            hK.copy_(full, non_blocking=True)
                     torch.cuda.synchronize()
                 e2e_s = e2e_timed(part, call)
-                h2d, d2h = m * 24, int(hK.numel())
-                del dIn, dLoc
+                h2d, d2h = m * 24 + (m if world > 1 else 0), m + (n if (rank == 0 and world > 1) else 0)
+                del dLoc
             else:
                 hK = pin(torch.empty(n, dtype=torch.uint8))
                 e2e_s = e2e_timed(part, lambda: Wt.eval(hQ.numpy(), want_w=False, out=(None, hK.numpy())))

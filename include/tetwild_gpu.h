@@ -208,6 +208,9 @@ int twg_winding_number(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_
  * (columns 1,2 swapped) and the test repeated; *retried tells which happened */
 int twg_inout_filter(twg_ctx* ctx, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, const double* C,
                      uint64_t nC, uint8_t* keep, int* retried);
+/* test hook: the three arrays of the hierarchy as they live on the device. nodes_out: n_nodes * 64 bytes, caps_out: n_cap_points * 4
+ * doubles, tris_out: (n_triangles + 2) * 9 doubles (sizes from twg_winding_stats; any pointer may be NULL) */
+int twg_debug_winding_download(twg_winding* w, void* nodes_out, double* caps_out, double* tris_out);
 /* statistics of the hierarchy: number of nodes, total cap segments, leaf triangles */
 int twg_winding_stats(const twg_winding* w, uint64_t* n_nodes, uint64_t* n_cap_segments, uint64_t* n_triangles);
 

@@ -70,7 +70,8 @@ def lst(path, out):
 def _num(v, unit=""):
     """ncu prints byte counts with a unit column (byte / Kbyte / Mbyte / Gbyte)"""
     x = float(str(v).replace(",", ""))
-    return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(unit, 1.0)
+    return x * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "nsecond": 1e-6, "usecond": 1e-3, "msecond": 1.0, "second": 1e3,
+                "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit, 1.0)
 
 
 def js(path, part, units, summary_file, out_json):
@@ -95,7 +96,7 @@ def js(path, part, units, summary_file, out_json):
          "issue_active_pct": get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
          "lanes_per_inst": get("smsp__thread_inst_executed_per_inst_executed.ratio"),
          "warps_active_pct": get("sm__warps_active.avg.pct_of_peak_sustained_active"),
-         "registers": get("launch__registers_per_thread"), "kernel_ms_under_ncu": (get("gpu__time_duration.sum") or 0) / 1e6 if d.get("gpu__time_duration.sum", ("", ""))[1] in ("ns", "nsecond") else get("gpu__time_duration.sum")}
+         "registers": get("launch__registers_per_thread"), "kernel_ms_under_ncu": get("gpu__time_duration.sum")}
     e = {k: v for k, v in e.items() if v is not None}
     try:
         allj = json.load(open(out_json))

@@ -16,11 +16,11 @@ EXE = os.path.join(ROOT, "tests", "_build", "wbuild_prof")
 def tool():
     src = os.path.join(ROOT, "tools", "wbuild_prof.cu")
     csrc = os.path.join(ROOT, "tetwild_b200", "csrc")
-    deps = [src, os.path.join(csrc, "winding.cu"), os.path.join(csrc, "common.cuh")]
+    deps = [src, os.path.join(csrc, "winding.cu"), os.path.join(csrc, "winding.cuh"), os.path.join(csrc, "winding_build.cu"), os.path.join(csrc, "common.cuh")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
         os.makedirs(os.path.dirname(EXE), exist_ok=True)
         subprocess.check_call(["nvcc", "-ccbin", "/usr/bin/g++", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "--expt-relaxed-constexpr",
-                               "-o", EXE, src, os.path.join(csrc, "ctx.cu"), os.path.join(csrc, "multi.cu"), os.path.join(csrc, "qsort.cu")], cwd=os.path.join(ROOT, "tools"))
+                               "-o", EXE, src, os.path.join(csrc, "ctx.cu"), os.path.join(csrc, "multi.cu"), os.path.join(csrc, "qsort.cu"), os.path.join(csrc, "winding_build.cu")], cwd=os.path.join(ROOT, "tools"))
     return EXE
 
 

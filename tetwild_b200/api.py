@@ -532,3 +532,12 @@ class Winding:
         a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
         self._L.twg_winding_stats(self.h, C.byref(a), C.byref(b), C.byref(c))
         return {"nodes": a.value, "cap_segments": b.value, "triangles": c.value}
+
+    def download(self):
+        """test hook: the hierarchy as it lives on the device -> (nodes as raw 64-byte records, caps [n,4], tris [nF+2,9])"""
+        st = self.stats()
+        nodes = np.empty((st["nodes"], 64), dtype=np.uint8)
+        caps = np.empty((st["cap_segments"], 4))
+        tris = np.empty((st["triangles"] + 2, 9))
+        self.ctx._check(self._L.twg_debug_winding_download(self.h, _ptr(nodes), _ptr(caps), _ptr(tris)))
+        return nodes, caps, tris

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtetwild_gpu.so")
-SOURCES = ["ctx.cu", "multi.cu", "qsort.cu", "amips.cu", "mesh.cu", "surface.cu", "envelope.cu", "winding.cu", "peaks.cu"]
-HEADERS = ["common.cuh", "tw_math.cuh", "winding_math.cuh", "surface.cuh", "sampling.cuh", os.path.join("..", "..", "include", "tetwild_gpu.h")]
+SOURCES = ["ctx.cu", "multi.cu", "qsort.cu", "amips.cu", "mesh.cu", "surface.cu", "envelope.cu", "winding.cu", "winding_build.cu", "peaks.cu"]
+HEADERS = ["common.cuh", "tw_math.cuh", "winding_math.cuh", "winding.cuh", "surface.cuh", "sampling.cuh", os.path.join("..", "..", "include", "tetwild_gpu.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

@@ -102,6 +102,13 @@ int twg_create(twg_ctx** out, int device_id) {
         return TWG_ERR_NO_DEVICE;
     }
     c->sm_count = prop.multiProcessorCount;
+    {   // the stream-ordered pool keeps what the device-side builds free (winding_build.cu), so a rebuild does not go back to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            unsigned long long keep = 1ull << 32;  // up to 4 GiB cached
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     c->lanes.reserve(TWG_MAX_LANES);
     for (int i = 0; i < TWG_NUM_STREAMS; ++i) {
         if (cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking) != cudaSuccess) { twg_destroy(c); return TWG_ERR_INTERNAL; }

@@ -30,6 +30,7 @@
 #include <thread>
 #include "common.cuh"
 #include "winding_math.cuh"
+#include "winding.cuh"
 
 namespace {
 
@@ -39,22 +40,6 @@ constexpr int kTilePts = 32;          // cap points per staged tile   (32 * 32 B
 constexpr int kTileTri = 32;          // triangles per staged tile    (32 * 72 B = 2304 B)
 constexpr int kStageBytes = 2304;
 constexpr int kStackDepth = 64;
-
-struct __align__(16) WNode {
-    float lo[3], hi[3];      // bounding box, rounded outward
-    uint32_t cap_off, cap_cnt;  // cap polyline points [cap_off, cap_off + cap_cnt) of WView::caps
-    double apex[3];
-    uint32_t tri_off, tri_cnt;  // facets of the whole subtree (contiguous in sorted order)
-};
-static_assert(sizeof(WNode) == 64, "WNode is 64 bytes");
-
-struct WView {
-    const WNode* nodes;    // heap, index 1 .. 2*nBlkP-1
-    const double* caps;    // 4 doubles per polyline point: x, y, z, flag (1.0 = first point of a chain)
-    const double* tris;    // 9 doubles per facet, sorted
-    uint32_t nBlkP;        // leaf blocks, power of two
-    uint32_t nF;
-};
 
 using tww::norm3;
 using tww::Angle;
@@ -234,13 +219,6 @@ struct CapRec {
 };
 
 
-struct HostTree {
-    std::vector<WNode> nodes;
-    std::vector<double> caps;
-    std::vector<double> tris;
-    uint32_t nBlkP = 1;
-};
-
 // ---- small host-side parallel helpers for the hierarchy build (std::thread, no OpenMP dependency)
 unsigned host_threads() {
     unsigned n = std::thread::hardware_concurrency();
@@ -380,6 +358,15 @@ void build_host_tree(const double* V, uint32_t nV, const uint32_t* F, uint32_t n
             for (auto& th : pool) th.join();
         }
     }
+    // canonical order inside every leaf block: by facet index. The kd splits fix which facets share a block (std::nth_element
+    // leaves their arrangement unspecified); sorting each block makes the facet array -- hence every sum -- a function of the
+    // input alone, and lets the device build (winding_build.cu) reproduce this hierarchy bit for bit.
+    parallel_ranges(nBlkP, host_threads(), [&](size_t b0, size_t b1, unsigned) {
+        for (size_t b = b0; b < b1; ++b) {
+            const uint64_t j0 = std::min<uint64_t>((uint64_t)b * kLeaf, nF), j1 = std::min<uint64_t>((uint64_t)(b + 1) * kLeaf, nF);
+            std::sort(order.begin() + j0, order.begin() + j1);
+        }
+    });
     std::vector<uint32_t> SF(3 * (size_t)nF);
     for (uint32_t j = 0; j < nF; ++j)
         for (int k = 0; k < 3; ++k) SF[3 * (size_t)j + k] = canon[F[3 * (size_t)order[j] + k]];
@@ -577,20 +564,6 @@ cudaStream_t pick(twg_ctx* c, void* stream) { return stream ? (cudaStream_t)stre
 
 }  // namespace
 
-struct twg_winding {
-    twg_ctx* ctx = nullptr;
-    WNode* nodes = nullptr;
-    double* caps = nullptr;
-    double* tris = nullptr;
-    uint32_t nBlkP = 1, nF = 0;
-    uint64_t n_nodes = 0, n_caps = 0;
-    uint32_t leaf = 64;  // triangles per leaf block (TWG_WINDING_LEAF)
-    double sort_box[6] = {0, 0, 0, 0, 0, 0};  // surface bbox grown by 10 %: Morton quantisation box of query batches
-    bool sort_queries = true;
-    std::vector<twg_winding*> replicas;  // handle made on a multi-device context: one replica per device
-    WView view() const { return WView{nodes, caps, tris, nBlkP, nF}; }
-};
-
 extern "C" {
 
 void twg_winding_destroy(twg_winding* w) {
@@ -637,10 +610,58 @@ static int winding_upload(twg_ctx* c, const HostTree& T, uint32_t nF, twg_windin
     return 0;
 }
 
+// surface to the device, hierarchy built there (winding_build.cu)
+static int winding_build_on_device(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out) {
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    double* dV = nullptr;
+    uint32_t* dF = nullptr;
+    TWG_CUDA(c, cudaMalloc(&dV, sizeof(double) * 3 * (size_t)nV));
+    cudaError_t e = cudaMalloc(&dF, sizeof(uint32_t) * 3 * (size_t)nF);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dV, V, sizeof(double) * 3 * (size_t)nV, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dF, F, sizeof(uint32_t) * 3 * (size_t)nF, cudaMemcpyHostToDevice, st);
+    DeviceTree T;
+    int rc = e == cudaSuccess ? twg_winding_build_device(c, dV, nV, dF, nF, (uint32_t)c->opt.winding_leaf, &T) : twg_fail(c, (int)e, cudaGetErrorString(e), __FILE__, __LINE__);
+    cudaStreamSynchronize(st);
+    cudaFree(dV);
+    cudaFree(dF);
+    if (rc != 0) { cudaFree(T.nodes); cudaFree(T.caps); cudaFree(T.tris); return rc; }
+    twg_winding* w = new twg_winding;
+    w->ctx = c;
+    w->nF = nF;
+    w->leaf = (uint32_t)c->opt.winding_leaf;
+    w->sort_queries = c->opt.winding_sort != 0;
+    w->nodes = T.nodes; w->caps = T.caps; w->tris = T.tris;
+    w->nBlkP = T.nBlkP; w->n_nodes = T.n_nodes; w->n_caps = T.n_caps;
+    for (int k = 0; k < 3; ++k) {
+        const double lo = T.root_lo[k], hi = T.root_hi[k], m = 0.1 * (hi - lo);
+        w->sort_box[k] = lo - m;
+        w->sort_box[3 + k] = hi + m;
+    }
+    *out = w;
+    return 0;
+}
+
 int twg_winding_create(twg_ctx* c, const double* V, uint32_t nV, const uint32_t* F, uint32_t nF, twg_winding** out) {
     TWG_CHECK(c, c && out && (nF == 0 || (V && F)), TWG_ERR_INVALID_ARG, "null argument");
     TWG_CHECK(c, nF < 0x7fffffffu, TWG_ERR_INVALID_ARG, "at most 2^31-2 facets");
     for (size_t k = 0; k < 3 * (size_t)nF; ++k) TWG_CHECK(c, F[k] < nV, TWG_ERR_INVALID_ARG, "facet references a vertex out of range");
+    if (nF && c->opt.winding_device_build) {  // the whole construction on the device (winding_build.cu); every device builds its own replica
+        if (twg_is_multi(c)) {
+            twg_winding* w = new twg_winding;
+            w->ctx = c;
+            w->nF = nF;
+            w->replicas.assign(c->children.size(), nullptr);
+            const int rc = twg_multi_run(c, [&](int k, twg_ctx* child) { return winding_build_on_device(child, V, nV, F, nF, &w->replicas[k]); });
+            if (rc != 0) { twg_winding_destroy(w); return rc; }
+            w->nBlkP = w->replicas[0]->nBlkP;
+            w->n_nodes = w->replicas[0]->n_nodes;
+            w->n_caps = w->replicas[0]->n_caps;
+            *out = w;
+            return 0;
+        }
+        return winding_build_on_device(c, V, nV, F, nF, out);
+    }
     HostTree T;
     if (nF) build_host_tree(V, nV, F, nF, (uint32_t)c->opt.winding_leaf, T);
     if (twg_is_multi(c)) {  // the hierarchy is built once and uploaded to every device by that device's thread
@@ -663,6 +684,20 @@ twg_winding* twg_winding_replica(twg_winding* w, int k) {
     if (!w) return nullptr;
     if (w->replicas.empty()) return k == 0 ? w : nullptr;
     return (k >= 0 && k < (int)w->replicas.size()) ? w->replicas[k] : nullptr;
+}
+
+// test hook: the three arrays of the hierarchy as they live on the device (replica 0 of a multi-device handle).
+// nodes_out: n_nodes * 64 bytes, caps_out: n_cap_points * 4 doubles, tris_out: (n_triangles + 2) * 9 doubles
+int twg_debug_winding_download(twg_winding* w, void* nodes_out, double* caps_out, double* tris_out) {
+    twg_ctx* c = w ? w->ctx : nullptr;
+    TWG_CHECK(c, w != nullptr, TWG_ERR_INVALID_ARG, "null argument");
+    if (!w->replicas.empty()) return twg_forward0(c, twg_debug_winding_download(w->replicas[0], nodes_out, caps_out, tris_out));
+    if (w->nF == 0) return 0;
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    if (nodes_out) TWG_CUDA(c, cudaMemcpy(nodes_out, w->nodes, w->n_nodes * sizeof(WNode), cudaMemcpyDeviceToHost));
+    if (caps_out) TWG_CUDA(c, cudaMemcpy(caps_out, w->caps, w->n_caps * 4 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (tris_out) TWG_CUDA(c, cudaMemcpy(tris_out, w->tris, ((size_t)w->nF + 2) * 9 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int twg_winding_stats(const twg_winding* w, uint64_t* n_nodes, uint64_t* n_caps, uint64_t* n_tris) {
