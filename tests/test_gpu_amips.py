@@ -119,26 +119,34 @@ def test_large_batch_properties(ctx, oracle):
     assert max(amips_close(T, (E2, J2, H2), (E, J, H))) < 1e-9
 
 
-def test_ring_kernels_prefetching_pipeline_equals_round1_kernel():
-    """Option ring_prefetch = 1 runs the one-ring kernel that prefetches the vertices of the next ring into L2 one pipeline stage
-    ahead (amips_ring_pf_kernel; measured slower, kept as an option); the default is the round-1 pipeline. Same members per lane, same reduction order: bit-identical
-    results, including rings of more than 32 tets, rejected rings and t_ids indirection."""
-    import tetwild_b200 as tw
+def test_ring_batches_do_not_depend_on_their_composition():
+    """A ring's sums depend on the ring alone: the same rings as one batch, as a sub-batch, through the t_ids indirection and
+    through the tiny-call path give the same bits. Rings of 0 .. 70 tets (empty rings, rings of more than 32 tets) and a
+    rejected ring."""
     V, tets, off, center = synth.ring_groups(5000, seed=21, kmin=3, kmax=70, scale_lo=0.1, scale_hi=10)
     V = V.copy()
     V[tets[int(off[11]) + 2, (list(tets[int(off[11]) + 2]).index(center[11]) + 1) % 4], 2] = np.nan
+    cnt = np.diff(off.astype(np.int64))
+    keep = np.ones(len(cnt), bool)
+    dropped = [100, 2000, 2001, 2002, len(cnt) - 1]
+    keep[dropped] = False
+    sel = np.repeat(keep, cnt)
+    tets = np.ascontiguousarray(tets[sel])
+    off = np.concatenate([[0], np.cumsum(np.where(keep, cnt, 0))]).astype(np.uint64)
     perm = np.random.default_rng(2).permutation(len(tets))
     inv = np.empty_like(perm)
     inv[perm] = np.arange(len(perm))
-    res = []
-    for mode in (1, 0):
-        c = tw.Context(0)
-        c.set_option("ring_prefetch", mode)
-        a = c.amips_ring_ejh(V, tets, off, center)
-        b = c.amips_ring_ejh(V, tets[perm], off, center, t_ids=inv.astype(np.int32))
-        e = c.amips_ring_energy(V, tets, off)
-        res.append((a, b, e))
-        c.close()
-    for x, y in zip(res[0][0] + res[0][1], res[1][0] + res[1][1]):
+    import tetwild_b200 as tw
+    c = tw.Context(0)
+    a = c.amips_ring_ejh(V, tets, off, center)
+    b = c.amips_ring_ejh(V, tets[perm], off, center, t_ids=inv.astype(np.int32))
+    sub = c.amips_ring_ejh(V, tets, off[:301], center[:300])
+    e = c.amips_ring_energy(V, tets, off)
+    c.close()
+    for x, y in zip(a, b):
         assert np.array_equal(x, y, equal_nan=True)
-    assert np.array_equal(res[0][2], res[1][2]) and res[0][0][3][11] == 0 and res[0][0][3].sum() == len(center) - 1
+    for x, y in zip(a, sub):
+        assert np.array_equal(x[:300], y, equal_nan=True)
+    okm = a[3]
+    assert okm[11] == 0 and okm.sum() == len(center) - 6 and not okm[dropped].any()
+    assert (e[dropped] == tw.MAX_ENERGY).all() and (a[0][dropped] == 0).all()

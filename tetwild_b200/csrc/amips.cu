@@ -204,20 +204,33 @@ __device__ __forceinline__ double warp_sum(double v) {
 //     transpose (10 stores + 16 loads per lane) instead of 13 x 5 64-bit shuffle steps; lane (c, h) adds the members
 //     16h .. 16h+15 of component c in lane order, the two halves meet in one shuffle -- deterministic, and closer to the
 //     reference's sequential ring order than a butterfly.
+//
+// Round 2 measured three other shapes of this kernel against it (profiles/r02_ring_variants.txt) and kept this one:
+//   * ncu (profiles/r02_amips_ring_kernel.txt): 21 warp instructions per tet at 58 % issue utilisation, FP64 pipe 30 %, L1 59 %,
+//     DRAM 34 % -- the kernel is bound by instruction issue and latency together, not by HBM; the closed-form evaluation is
+//     only ~200 of the ~520 instructions a ring costs, the rest is gather, address chain and reduction;
+//   * vertices of ring i+1 staged in shared memory with cp.async, or prefetched into L2: 11.7 / 17.2 G tets/s (more
+//     instructions than the latency they hide);
+//   * rings of a warp walked as ONE dense member stream, 32 members per step, in-order segmented reduction in shared memory:
+//     lanes full (31.4 in the evaluation) but 340 instructions per step of reduction: 25 instructions per tet, 24.8 G tets/s
+//     (profiles/r02_amips_ring_flat_kernel_not_kept.txt);
+//   * one ring per LANE, members added in registers (no reduction at all, 12.9 instructions per tet): 29.1 G tets/s on 16 M
+//     tets, but every lane is then its own memory stream -- 113 664 of them -- and beyond ~25 M tets (2 GB of mesh) the kernel
+//     drops to 6.4 G tets/s with every unit idle (DRAM 9 %, L1 16 %, issue 34 %, long-scoreboard 10.8: profiles/
+//     r02_amips_ring_lane_kernel_not_kept.txt), whether a lane's rings are interleaved or consecutive.
 struct RingHead {   // stage result: CSR bounds and centre of one ring (member offsets fit 32 bits: at most 4 * 2^29 members)
     uint32_t b, cnt;
     int32_t c;
 };
 
-template <bool ENERGY_ONLY, int MINB>
-__global__ void __launch_bounds__(256, MINB) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
-                                                            const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
-                                                            const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
-                                                            double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
-                                                            uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg,
-                                                            const double* __restrict__ trial) {
+// `vids` and `trial` are read with plain loads: the tiny-call kernel below passes them in shared memory
+template <bool ENERGY_ONLY>
+__device__ __forceinline__ void ring_warp_body(const double* __restrict__ V, const int4* __restrict__ tets, const int32_t* __restrict__ t_ids,
+                                               const uint64_t* __restrict__ off, const int32_t* __restrict__ center, const int32_t* vids, uint64_t nG,
+                                               double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9, uint8_t* __restrict__ ok,
+                                               uint32_t nV, uint64_t nT, unsigned long long* dbg, const double* trial) {
     constexpr int NRED = ENERGY_ONLY ? 1 : 10;
-    __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
+    __shared__ double red[8][NRED][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(256, MINB) amips_ring_kernel(const double* __r
     // ---- pipeline stages: straight-line, every load unconditional or predicated (no branches)
     auto stage_row = [&](uint64_t g) -> uint32_t {  // vids != NULL: ring g is the one-ring of vertex vids[g] in a vertex -> tets CSR
         const uint64_t gg = g < gl ? g : gl;
-        return vids ? (uint32_t)__ldg(vids + gg) : (uint32_t)gg;
+        return vids ? (uint32_t)vids[gg] : (uint32_t)gg;
     };
     auto stage_head = [&](uint64_t g, uint32_t row) -> RingHead {
         const uint64_t gg = g < gl ? g : gl;
@@ -250,7 +263,7 @@ __global__ void __launch_bounds__(256, MINB) amips_ring_kernel(const double* __r
     // vertex, asks getNewEnergy, and moves it back -- here the mesh stays untouched and the ring sees the vertex at `trial`)
     uint64_t g_cur = 0;
     auto override_centre = [&](double* x, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int32_t c) {
-        const double tx = __ldg(trial + 3 * g_cur), ty = __ldg(trial + 3 * g_cur + 1), tz = __ldg(trial + 3 * g_cur + 2);
+        const double tx = trial[3 * g_cur], ty = trial[3 * g_cur + 1], tz = trial[3 * g_cur + 2];
         const int32_t a[4] = {a0, a1, a2, a3};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -358,174 +371,36 @@ __global__ void __launch_bounds__(256, MINB) amips_ring_kernel(const double* __r
     }
 }
 
-// amips_ring_kernel with the VERTEX GATHER announced one ring ahead (round 2). In the kernel above a ring's last dependent
-// load -- the 72 B of its members' vertices -- is the one the warp waits for (ncu r01: long_scoreboard 2.8, 0.41 of the HBM peak
-// at 94 B/tet of traffic: no wasted bytes, only latency). Here the tet records arrive one iteration earlier (one more
-// pipeline stage) and every lane PREFETCHES the vertices of its member of ring i+1 into L2 (prefetch.global.L2: no register,
-// no shared memory) before it gathers and evaluates its member of ring i, whose lines then come from L2 instead of HBM.
-// Stages per iteration: row(i+5), CSR bounds(i+4), member ids(i+3), tet records(i+2), vertex prefetch(i+1), gather + evaluate(i).
-// Measured and NOT kept (r2s6): staging the vertices in shared memory with cp.async (8 B per copy, a vertex is only 8-byte
-// aligned): 11.7 instead of 28.0 G tets/s, long_scoreboard 13.9 -- 384 LDGSTS per warp and ring cost more than they hide.
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <bool ENERGY_ONLY, int MINB>
+__global__ void __launch_bounds__(256, MINB) amips_ring_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
+                                                            const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
+                                                            const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
+                                                            double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
+                                                            uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg,
+                                                            const double* __restrict__ trial) {
+    ring_warp_body<ENERGY_ONLY>(V, tets, t_ids, off, center, vids, nG, E, J3, H9, ok, nV, nT, dbg, trial);
+}
 
+// The tiny call of the sequential scheduler (ONE Newton step, the step sizes of ONE line search: twg_mesh_vertex_ring_ejh /
+// twg_mesh_vertex_trial_energy with n <= 32): the vertex ids and trial positions travel in the kernel's PARAMETERS (no read
+// over PCIe, no copy), the results go straight to the mapped slab and the last CTA raises the completion word itself (no
+// second launch): one driver call per host call.
+struct TwgTinyRings {
+    int32_t vid[32];
+    double xyz[96];
+};
 template <bool ENERGY_ONLY>
-__global__ void __launch_bounds__(256, 3) amips_ring_pf_kernel(const double* __restrict__ V, const int4* __restrict__ tets,
-                                                               const int32_t* __restrict__ t_ids, const uint64_t* __restrict__ off,
-                                                               const int32_t* __restrict__ center, const int32_t* __restrict__ vids, uint64_t nG,
-                                                               double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
-                                                               uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg,
-                                                               const double* __restrict__ trial) {
-    constexpr int NRED = ENERGY_ONLY ? 1 : 10;
-    __shared__ double red[ENERGY_ONLY ? 1 : 8][NRED][33];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    const uint64_t gl = nG - 1;  // prefetches past the end re-read the last ring (valid addresses, never consumed)
-
-    auto stage_row = [&](uint64_t g) -> uint32_t {
-        const uint64_t gg = g < gl ? g : gl;
-        return vids ? (uint32_t)__ldg(vids + gg) : (uint32_t)gg;
-    };
-    auto stage_head = [&](uint64_t g, uint32_t row) -> RingHead {
-        const uint64_t gg = g < gl ? g : gl;
-        const uint64_t b = __ldg(off + row), e = __ldg(off + row + 1);
-        RingHead h;
-        h.b = (uint32_t)b; h.cnt = (uint32_t)(e - b);
-        h.c = vids ? (int32_t)row : (ENERGY_ONLY ? 0 : __ldg(center + gg));
-        return h;
-    };
-    auto stage_tid = [&](const RingHead& h, uint32_t k) -> uint32_t {
-        const bool in = k < h.cnt;
-        return t_ids ? (in ? (uint32_t)__ldg(t_ids + h.b + k) : 0u) : h.b + (in ? k : 0u);
-    };
-    auto stage_tet = [&](const RingHead& h, uint32_t k, uint32_t ti) -> int4 {
-        int4 t = make_int4(-1, -1, -1, -1);
-        if (k < h.cnt && (uint64_t)ti < nT) t = __ldg(tets + ti);
-        return t;
-    };
-    // stage "vertex prefetch": the lane's member of a later ring -> L2 (first and last double of every vertex: a 24-byte vertex
-    // may straddle two lines)
-    auto stage_prefetch = [&](const RingHead& h, int4 t) {
-        if ((uint32_t)lane < h.cnt && (uint32_t)t.x < nV && (uint32_t)t.y < nV && (uint32_t)t.z < nV && (uint32_t)t.w < nV) {
-            const int32_t a[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                const double* src = V + 3 * (size_t)a[v];
-                prefetch_l2(src);
-                prefetch_l2(src + 2);
-            }
-        }
-    };
-    // trial position of the centre vertex (twg_mesh_vertex_trial_energy: the line search of VertexSmoother.cpp:505-541 moves the
-    // vertex, asks getNewEnergy, and moves it back -- here the mesh stays untouched and the ring sees the vertex at `trial`)
-    uint64_t g_cur = 0;
-    auto override_centre = [&](double* x, int32_t a0, int32_t a1, int32_t a2, int32_t a3, int32_t c) {
-        const double tx = __ldg(trial + 3 * g_cur), ty = __ldg(trial + 3 * g_cur + 1), tz = __ldg(trial + 3 * g_cur + 2);
-        const int32_t a[4] = {a0, a1, a2, a3};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (a[j] == c) { x[3 * j] = tx; x[3 * j + 1] = ty; x[3 * j + 2] = tz; }
-    };
-    auto member = [&](int4 t, int32_t c, double* acc) {
-        int32_t a0 = t.x, a1 = t.y, a2 = t.z, a3 = t.w;
-        // removed slots (negative first index) and out-of-range ids contribute nothing and are never dereferenced
-        if ((uint32_t)a0 >= nV || (uint32_t)a1 >= nV || (uint32_t)a2 >= nV || (uint32_t)a3 >= nV) {
-            atomicAdd(dbg + TWG_DBG_BAD_INDEX, 1ull);
-            return;
-        }
-        if (!ENERGY_ONLY) {  // :640-651, centre to slot 0
-            const int start = (a0 == c) ? 0 : (a1 == c) ? 1 : (a2 == c) ? 2 : (a3 == c) ? 3 : 0;
-            const bool r1 = (start & 1) != 0, r2 = (start & 2) != 0;
-            const int32_t b0 = r1 ? a1 : a0, b1 = r1 ? a2 : a1, b2 = r1 ? a3 : a2, b3 = r1 ? a0 : a3;
-            a0 = r2 ? b2 : b0; a1 = r2 ? b3 : b1; a2 = r2 ? b0 : b2; a3 = r2 ? b1 : b3;
-        }
-        double x[12];
-        gather_vertex(V, a0, x);
-        gather_vertex(V, a1, x + 3);
-        gather_vertex(V, a2, x + 6);
-        gather_vertex(V, a3, x + 9);
-        if (trial) override_centre(x, a0, a1, a2, a3, c);
-        tw::Amips r;
-        tw::amips_eval<!ENERGY_ONLY>(x, r);
-        acc[0] += r.E;
-        if (!ENERGY_ONLY) {
-            acc[1] += r.J[0]; acc[2] += r.J[1]; acc[3] += r.J[2];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) acc[4 + k] += r.H[k];
-        }
-    };
-
-    // ---- prologue
-    uint64_t g = warp;
-    RingHead h_cur = stage_head(g, stage_row(g));
-    int4 tet_cur = stage_tet(h_cur, lane, stage_tid(h_cur, lane));
-    RingHead h_n1 = stage_head(g + nwarps, stage_row(g + nwarps));
-    int4 tet_n1 = stage_tet(h_n1, lane, stage_tid(h_n1, lane));
-    RingHead h_n2 = stage_head(g + 2 * nwarps, stage_row(g + 2 * nwarps));
-    uint32_t ti_n2 = stage_tid(h_n2, lane);
-    RingHead h_n3 = stage_head(g + 3 * nwarps, stage_row(g + 3 * nwarps));
-    uint32_t row_n4 = stage_row(g + 4 * nwarps);
-
-    for (; g < nG; g += nwarps) {
-        g_cur = g;
-        // ---- issue the loads of the later rings first
-        const uint32_t row_n5 = stage_row(g + 5 * nwarps);
-        const RingHead h_n4 = stage_head(g + 4 * nwarps, row_n4);
-        const uint32_t ti_n3 = stage_tid(h_n3, lane);
-        const int4 tet_n2 = stage_tet(h_n2, lane, ti_n2);
-        stage_prefetch(h_n1, tet_n1);
-        // ---- ring g
-        double acc[NRED];
-#pragma unroll
-        for (int k = 0; k < NRED; ++k) acc[k] = 0.0;
-        if ((uint32_t)lane < h_cur.cnt) member(tet_cur, h_cur.c, acc);
-        for (uint32_t k = 32 + lane; k < h_cur.cnt; k += 32)  // rings of more than 32 tets: the rest is fetched on demand
-            member(stage_tet(h_cur, k, stage_tid(h_cur, k)), h_cur.c, acc);
-        if (ENERGY_ONLY) {
-            double en = warp_sum(acc[0]);
-            if (lane == 0) {  // getNewEnergy :619-622
-                if (isinf(en) || isnan(en) || en <= 0.0 || en > TWG_MAX_ENERGY) en = TWG_MAX_ENERGY;
-                E[g] = en;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NRED; ++k) red[wib][k][lane] = acc[k];
-            __syncwarp();
-            const int cmp = lane & 15, half = lane >> 4;
-            double sum = 0.0;
-            if (cmp < NRED) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) sum += red[wib][cmp][half * 16 + j];
-            }
-            sum += __shfl_xor_sync(0xffffffffu, sum, 16);
-            __syncwarp();
-            bool bad = false;
-            if (cmp == 0) {
-                if (isinf(sum)) sum = TWG_MAX_ENERGY;
-                bad = isnan(sum) || sum <= 0.0;
-            } else if (cmp < NRED) {
-                bad = !isfinite(sum);
-            }
-            const bool good = !__any_sync(0xffffffffu, bad);
-            if (half == 0) {
-                if (cmp == 0) { E[g] = sum; if (ok) ok[g] = good ? 1 : 0; }
-                else if (cmp < 4) J3[g * 3 + (cmp - 1)] = sum;
-                else if (cmp < NRED) {
-                    const int s0 = (cmp == 4) ? 0 : (cmp == 5) ? 1 : (cmp == 6) ? 2 : (cmp == 7) ? 4 : (cmp == 8) ? 5 : 8;
-                    const int s1 = (cmp == 5) ? 3 : (cmp == 6) ? 6 : (cmp == 8) ? 7 : s0;
-                    double* Hg = H9 + g * 9;
-                    Hg[s0] = sum;
-                    Hg[s1] = sum;
-                }
-            }
-        }
-        // ---- advance the pipeline
-        h_cur = h_n1; tet_cur = tet_n1;
-        h_n1 = h_n2; tet_n1 = tet_n2;
-        h_n2 = h_n3; ti_n2 = ti_n3;
-        h_n3 = h_n4;
-        row_n4 = row_n5;
-    }
+__global__ void __launch_bounds__(256, 3) amips_ring_tiny_kernel(const double* __restrict__ V, const int4* __restrict__ tets, const int32_t* __restrict__ adj,
+                                                                 const uint64_t* __restrict__ off, const __grid_constant__ TwgTinyRings in, uint32_t n,
+                                                                 double* __restrict__ E, double* __restrict__ J3, double* __restrict__ H9,
+                                                                 uint8_t* __restrict__ ok, uint32_t nV, uint64_t nT, unsigned long long* dbg, twg_done done) {
+    __shared__ int32_t sv[32];
+    __shared__ double sx[96];
+    if (threadIdx.x < 32) sv[threadIdx.x] = in.vid[threadIdx.x];
+    if (ENERGY_ONLY && threadIdx.x < 96) sx[threadIdx.x] = in.xyz[threadIdx.x];
+    __syncthreads();
+    ring_warp_body<ENERGY_ONLY>(V, tets, adj, off, nullptr, sv, n, E, J3, H9, ok, nV, nT, dbg, ENERGY_ONLY ? sx : nullptr);
+    twg_signal_done(done);
 }
 
 inline bool aligned16(const void* p) { return (((uintptr_t)p) & 15u) == 0; }
@@ -589,11 +464,6 @@ template <bool ENERGY_ONLY>
 int launch_ring(twg_ctx* c, cudaStream_t st, const double* dV, uint32_t nV, const int4* dTets, uint64_t nT, const int32_t* dTids, const uint64_t* dOff,
                 const int32_t* dCenter, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3, double* dH9, uint8_t* dOk,
                 const double* dTrial = nullptr) {
-    if (c->opt.ring_prefetch) {
-        TWG_LAUNCH(c, (amips_ring_pf_kernel<ENERGY_ONLY>), grid_for(c, nG, 8, ring_waves(c)), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids, nG, dE, dJ3, dH9,
-                   dOk, nV, nT, c->dcounters, dTrial);
-        return 0;
-    }
     if (c->opt.ring_minb >= 4) {  // 64 registers, 32 warps per SM
         TWG_LAUNCH(c, (amips_ring_kernel<ENERGY_ONLY, 4>), grid_for(c, nG, 8, ring_waves(c) > 4 ? ring_waves(c) : 4), 256, 0, st, dV, dTets, dTids, dOff, dCenter, dVids,
                    nG, dE, dJ3, dH9, dOk, nV, nT, c->dcounters, dTrial);
@@ -653,6 +523,28 @@ int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint32_t nV, con
     TWG_CHECK(c, !twg_is_multi(c), TWG_ERR_INVALID_ARG, "_dev entry points take a one-device context (twg_device_context)");
     TWG_CUDA(c, cudaSetDevice(c->device));
     return launch_ring<false>(c, pick(c, stream), dV, nV, (const int4*)dTets, nT, dAdjTets, dAdjOff, (const int32_t*)nullptr, dVids, nG, dE, dJ3, dH9, dOk);
+}
+
+// n <= 32 one-rings of the resident mesh named by HOST vertex ids; trial_xyz != NULL: getNewEnergy with the vertex at the trial
+// position (energies only), else NewtonsUpdate's E / J / H / ok. Output pointers are device-visible (the mapped slab).
+int twg_amips_ring_tiny(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets, const uint64_t* dAdjOff,
+                        const int32_t* v_ids, const double* trial_xyz, uint32_t n, double* E, double* J3, double* H9, uint8_t* ok, cudaStream_t st,
+                        const twg_done* done) {
+    TWG_CHECK(c, c && dV && dTets && dAdjTets && dAdjOff && v_ids && E && done && n >= 1 && n <= 32, TWG_ERR_INVALID_ARG, "bad tiny ring call");
+    TWG_CHECK(c, aligned16(dTets), TWG_ERR_ALIGNMENT, "tets4 must be 16-byte aligned");
+    TwgTinyRings in;
+    memcpy(in.vid, v_ids, (size_t)n * 4);
+    for (uint32_t k = n; k < 32; ++k) in.vid[k] = v_ids[0];
+    const unsigned blocks = (n + 7) / 8;
+    if (trial_xyz) {
+        memcpy(in.xyz, trial_xyz, (size_t)n * 24);
+        TWG_LAUNCH(c, (amips_ring_tiny_kernel<true>), blocks, 256, 0, st, dV, (const int4*)dTets, dAdjTets, dAdjOff, in, n, E, (double*)nullptr, (double*)nullptr,
+                   (uint8_t*)nullptr, nV, nT, c->dcounters, *done);
+    } else {
+        TWG_CHECK(c, J3 && H9, TWG_ERR_INVALID_ARG, "null argument");
+        TWG_LAUNCH(c, (amips_ring_tiny_kernel<false>), blocks, 256, 0, st, dV, (const int4*)dTets, dAdjTets, dAdjOff, in, n, E, J3, H9, ok, nV, nT, c->dcounters, *done);
+    }
+    return 0;
 }
 
 // getNewEnergy of the one-ring of vertex dVids[g] with that vertex at dTrial[3g..3g+2] (the mesh itself is not modified)

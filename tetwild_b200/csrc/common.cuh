@@ -27,7 +27,6 @@ struct twg_options {
     int sort_curve = 0;        // query order: 0 Z (Morton) curve, 1 Hilbert curve
     long long chunk_points = 1ll << 20;  // points per staging chunk of the host entry points
     int ring_waves = 3;        // resident CTAs per SM of the one-ring kernels
-    int ring_prefetch = 0;     // one-ring kernels prefetch the vertices of the next ring into L2 (measured slower: 17 vs 28 G tets/s)
     int ring_minb = 3;         // resident CTAs per SM the one-ring kernel's registers are capped for (3: 80 registers, 4: 64)
     int winding_minb = 3;
     int winding_sort = 1;
@@ -74,6 +73,7 @@ struct twg_ctx {
     void* fast_slab = nullptr;
     size_t fast_bytes = 0;
     uint32_t fast_seq = 0;
+    uint32_t* fast_counter = nullptr;  // device: CTAs of the tiny kernel in flight that are through (twg_signal_done)
     std::vector<twg_lane> lanes;
     uint64_t lane_tick = 0;
     unsigned long long* dcounters = nullptr;  // device, TWG_NUM_DEBUG_COUNTERS slots (twg_debug_counter)
@@ -128,6 +128,31 @@ int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
 // twg_fast_slab returns the slab (host pointer == device pointer under unified addressing), at least `bytes` long.
 int twg_fast_slab(twg_ctx* c, size_t bytes, char** slab);
 int twg_fast_wait(twg_ctx* c, cudaStream_t st);
+// The same without the second launch: a kernel that takes a twg_done raises the completion word itself when its last CTA is
+// through (twg_signal_done as the kernel's last statement, reached by every thread). twg_fast_arm hands out the word, the
+// CTA counter and the sequence number for ONE launch on `st`; twg_fast_spin waits for that number.
+struct twg_done {
+    volatile uint32_t* flag;  // NULL: nothing to signal
+    uint32_t* counter;        // device memory, zero between launches
+    uint32_t seq;
+};
+int twg_fast_arm(twg_ctx* c, twg_done* done);
+int twg_fast_spin(twg_ctx* c, cudaStream_t st, uint32_t seq);
+#ifdef __CUDACC__
+__device__ __forceinline__ void twg_signal_done(const twg_done& d) {
+    if (!d.flag) return;
+    __threadfence_system();  // this thread's results are visible to the host before the word is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y * gridDim.z;
+        if (total == 1u || atomicAdd(d.counter, 1u) == total - 1u) {
+            if (total != 1u) *d.counter = 0u;
+            __threadfence_system();
+            *d.flag = d.seq;
+        }
+    }
+}
+#endif
 int twg_ensure_pinned(twg_ctx* c, size_t in_bytes, size_t out_bytes);
 #define TWG_SORT_MIN 4096  /* batches below this are traversed in the caller's order */
 // the lane of stream `st` (created on first use); *out stays valid until the next twg_get_lane call on this context

@@ -25,7 +25,6 @@ const OptDesc kOpts[] = {
     {"sort_curve", &twg_options::sort_curve, nullptr, 0, 1},
     {"chunk_points", nullptr, &twg_options::chunk_points, 1024, 1ll << 31},
     {"ring_waves", &twg_options::ring_waves, nullptr, 1, 32},
-    {"ring_prefetch", &twg_options::ring_prefetch, nullptr, 0, 1},
     {"ring_minb", &twg_options::ring_minb, nullptr, 3, 4},
     {"winding_minb", &twg_options::winding_minb, nullptr, 1, 8},
     {"winding_sort", &twg_options::winding_sort, nullptr, 0, 1},
@@ -148,6 +147,7 @@ void twg_destroy(twg_ctx* c) {
     }
     if (c->dcounters) cudaFree(c->dcounters);
     if (c->fast_slab) cudaFreeHost(c->fast_slab);
+    if (c->fast_counter) cudaFree(c->fast_counter);
     delete c;
 }
 
@@ -274,12 +274,32 @@ int twg_fast_slab(twg_ctx* c, size_t bytes, char** slab) {
     return 0;
 }
 
+int twg_fast_arm(twg_ctx* c, twg_done* done) {
+    if (!c->fast_counter) {
+        TWG_CUDA(c, cudaMalloc(&c->fast_counter, 256));
+        TWG_CUDA(c, cudaMemset(c->fast_counter, 0, 256));
+    }
+    if (!c->fast_slab) {
+        char* slab;
+        TWG_TRY(twg_fast_slab(c, 0, &slab));
+    }
+    done->flag = (volatile uint32_t*)c->fast_slab;
+    done->counter = c->fast_counter;
+    done->seq = ++c->fast_seq ? c->fast_seq : ++c->fast_seq;  // never 0
+    return 0;
+}
+
 int twg_fast_wait(twg_ctx* c, cudaStream_t st) {
     volatile uint32_t* flag = (volatile uint32_t*)c->fast_slab;
     const uint32_t seq = ++c->fast_seq ? c->fast_seq : ++c->fast_seq;  // never 0
     fast_signal_kernel<<<1, 32, 0, st>>>(flag, seq);
     c->launches++;
     TWG_CUDA(c, cudaGetLastError());
+    return twg_fast_spin(c, st, seq);
+}
+
+int twg_fast_spin(twg_ctx* c, cudaStream_t st, uint32_t seq) {
+    volatile uint32_t* flag = (volatile uint32_t*)c->fast_slab;
     // spin: the word arrives over PCIe right after the results (posted writes of one device stay in order)
     for (unsigned long long spins = 0; *flag != seq; ++spins) {
         if ((spins & 0xfffff) == 0xfffff) {  // ~ every few ms: has the stream failed?

@@ -329,6 +329,41 @@ __global__ void __launch_bounds__(kEnvThreads, 8) nearest_kernel(SurfaceView S, 
     }
 }
 
+// The tiny call of the sequential scheduler (ONE point: EdgeCollapser.cpp:312,322; VertexSmoother.cpp:358; n <= 64): the points
+// travel in the kernel's parameters, one lane per point walks the tree on its own (in_envelope / nearest_facet, the routines the
+// face kernel and the per-lane nearest kernel use: same exact predicates, same answers), results go straight into the mapped
+// slab and the kernel raises the completion word itself -- ONE driver call per host call (the batched path needs a counter reset,
+// the kernel and a signal launch).
+struct TwgTinyPoints {
+    double xyz[192];
+};
+__global__ void __launch_bounds__(64) points_tiny_kernel(SurfaceView S, const __grid_constant__ TwgTinyPoints in, uint32_t n, int what, double eps2,
+                                                         uint8_t* __restrict__ out, uint32_t* __restrict__ facet, double* __restrict__ nearest,
+                                                         double* __restrict__ d2out, twg_done done) {
+    const uint32_t i = threadIdx.x;
+    if (i < n) {
+        const tw::V3 p = tw::mk(in.xyz[3 * i], in.xyz[3 * i + 1], in.xyz[3 * i + 2]);
+        if (what == 0) {
+            uint32_t pos;
+            out[i] = twd::in_envelope(S, p, eps2, pos, nullptr, 0u) ? 0 : 1;
+        } else {
+            twd::Nearest b;
+            b.d2 = DBL_MAX; b.s = b.t = 0.0; b.pos = 0; b.deg = false; b.pt_deg = p;
+            twd::nearest_facet(S, p, b, nullptr, 0u);
+            if (d2out) d2out[i] = b.d2;
+            if (facet || nearest) {
+                const tw::TriRec r = twd::load_tri(S.tris + b.pos);
+                if (facet) facet[i] = r.facet;
+                if (nearest) {
+                    const tw::V3 q = b.deg ? b.pt_deg : tw::tri_nearest_point(r, b.s, b.t);
+                    nearest[3 * i] = q.x; nearest[3 * i + 1] = q.y; nearest[3 * i + 2] = q.z;
+                }
+            }
+        }
+    }
+    twg_signal_done(done);
+}
+
 // Exact nearest facet for large sorted batches (nearest_facet, mesh_AABB.cpp:418-480): two warp-cooperative forms, no per-thread
 // stack anywhere (round 1: one descent per lane with two 32-entry stacks in local memory -- 9.7 active lanes per instruction,
 // 232 M local-memory accesses per 10 M points).
@@ -943,8 +978,10 @@ struct __align__(16) FaceRun {
     int off;            // samples before this run (exclusive scan)
 };
 
-__global__ void __launch_bounds__(kEnvThreads, 4) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
-                                                               uint32_t flags, uint8_t* __restrict__ out) {
+// LDG: `tris` is global memory (read-only path); else it may be shared memory (the tiny-call kernel below): plain loads
+template <bool LDG>
+__device__ __forceinline__ void env_faces_body(const SurfaceView& S, const double* tris, uint64_t n, double sd, double eps2, uint32_t flags,
+                                               uint8_t* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smraw[];
     NodePair* top = reinterpret_cast<NodePair*>(smraw);
     __shared__ __align__(8) uint64_t bar;
@@ -962,7 +999,7 @@ __global__ void __launch_bounds__(kEnvThreads, 4) env_faces_kernel(SurfaceView S
     for (uint64_t f = warp; f < n; f += nwarps) {
         double t9[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) t9[k] = __ldg(tris + f * 9 + k);
+        for (int k = 0; k < 9; ++k) t9[k] = LDG ? __ldg(tris + f * 9 + k) : tris[f * 9 + k];
         // :1048 -- Preprocess::isOutEnvelop (Preprocess.cpp:643-747) has no such shortcut
         if (!(flags & TWG_FACES_NO_DEGENERATE_SHORTCUT) && tw::exact::triangle_is_degenerate(t9, t9 + 3, t9 + 6)) {
             if (lane == 0) out[f] = 0;
@@ -1140,6 +1177,25 @@ __global__ void __launch_bounds__(kEnvThreads, 4) env_faces_kernel(SurfaceView S
     }
 }
 
+__global__ void __launch_bounds__(kEnvThreads, 4) env_faces_kernel(SurfaceView S, const double* __restrict__ tris, uint64_t n, double sd, double eps2,
+                                                               uint32_t flags, uint8_t* __restrict__ out) {
+    env_faces_body<true>(S, tris, n, sd, eps2, flags, out);
+}
+
+// The faces of ONE candidate operation (EdgeCollapser.cpp:770, VertexSmoother.cpp:425; n <= 16): the triangles travel in the
+// kernel's parameters, the decisions go straight into the mapped slab, the last CTA raises the completion word itself.
+struct TwgTinyFaces {
+    double tri[16 * 9];
+};
+__global__ void __launch_bounds__(kEnvThreads, 4) env_faces_tiny_kernel(SurfaceView S, const __grid_constant__ TwgTinyFaces in, uint32_t n, double sd, double eps2,
+                                                                    uint32_t flags, uint8_t* __restrict__ out, twg_done done) {
+    __shared__ double st[16 * 9];
+    for (int i = threadIdx.x; i < 16 * 9; i += blockDim.x) st[i] = in.tri[i];
+    __syncthreads();
+    env_faces_body<false>(S, st, n, sd, eps2, flags, out);
+    twg_signal_done(done);
+}
+
 struct CollectSink {
     double* out;
     uint64_t cap, n;
@@ -1281,14 +1337,13 @@ static int points_host(twg_surface* s, int what, const double* P, uint64_t n, do
         const size_t qb = up(n * 24), rb = up(n), fb2 = up(n * 4), nb2 = up(n * 24), db2 = up(n * 8);
         TWG_TRY(twg_fast_slab(c, qb + rb + fb2 + nb2 + db2, &slab));
         cudaStream_t st = c->streams[0];
-        memcpy(slab, P, n * 24);
-        if (what == 0) {
-            TWG_TRY(twg_envelope_points_out_dev(s, (const double*)slab, n, eps2, (uint8_t*)(slab + qb), st));
-        } else {
-            TWG_TRY(twg_nearest_dev(s, (const double*)slab, n, facet ? (uint32_t*)(slab + qb + rb) : nullptr, nearest ? (double*)(slab + qb + rb + fb2) : nullptr,
-                                    d2 ? (double*)(slab + qb + rb + fb2 + nb2) : nullptr, st));
-        }
-        TWG_TRY(twg_fast_wait(c, st));
+        TwgTinyPoints in;
+        memcpy(in.xyz, P, n * 24);
+        twg_done done;
+        TWG_TRY(twg_fast_arm(c, &done));
+        TWG_LAUNCH(c, points_tiny_kernel, 1, 64, 0, st, view_of(s), in, (uint32_t)n, what, eps2, (uint8_t*)(slab + qb), facet ? (uint32_t*)(slab + qb + rb) : nullptr,
+                   nearest ? (double*)(slab + qb + rb + fb2) : nullptr, d2 ? (double*)(slab + qb + rb + fb2 + nb2) : nullptr, done);
+        TWG_TRY(twg_fast_spin(c, st, done.seq));
         if (what == 0) memcpy(out, slab + qb, n);
         if (facet) memcpy(facet, slab + qb + rb, n * 4);
         if (nearest) memcpy(nearest, slab + qb + rb + fb2, n * 24);
@@ -1367,9 +1422,15 @@ int twg_envelope_faces_out_ex(twg_surface* s, const double* tris, uint64_t n, do
         char* slab;
         TWG_TRY(twg_fast_slab(c, up(n * 72) + up(n), &slab));
         cudaStream_t st = c->streams[0];
-        memcpy(slab, tris, n * 72);
-        TWG_TRY(twg_envelope_faces_out_ex_dev(s, (const double*)slab, n, sd, eps2, flags, (uint8_t*)(slab + up(n * 72)), st));
-        TWG_TRY(twg_fast_wait(c, st));
+        TWG_CHECK(c, eps2 >= 0.0 && sd > 0.0 && isfinite(sd), TWG_ERR_INVALID_ARG, "need eps2 >= 0 and finite sampling_dist > 0");
+        TwgTinyFaces in;
+        memcpy(in.tri, tris, n * 72);
+        twg_done done;
+        TWG_TRY(twg_fast_arm(c, &done));
+        // one warp per face, kEnvThreads / 32 warps per CTA
+        TWG_LAUNCH(c, env_faces_tiny_kernel, (unsigned)((n + kEnvThreads / 32 - 1) / (kEnvThreads / 32)), kEnvThreads, top_smem(s), st, view_of(s), in, (uint32_t)n, sd, eps2,
+                   flags, (uint8_t*)(slab + up(n * 72)), done);
+        TWG_TRY(twg_fast_spin(c, st, done.seq));
         memcpy(out, slab + up(n * 72), n);
         return 0;
     }

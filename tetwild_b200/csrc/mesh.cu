@@ -18,6 +18,12 @@ extern "C" int twg_amips_vertex_ring_ejh_dev(twg_ctx* c, const double* dV, uint3
                                              const uint64_t* dAdjOff, const int32_t* dVids, uint64_t nG, double* dE, double* dJ3,
                                              double* dH9, uint8_t* dOk, void* stream);
 
+// tiny-call variant (amips.cu): n <= 32 rings named by HOST vertex ids (and host trial positions -> energies only), results
+// into the mapped slab, completion through `done`
+extern "C" int twg_amips_ring_tiny(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets, const uint64_t* dAdjOff,
+                                   const int32_t* v_ids, const double* trial_xyz, uint32_t n, double* E, double* J3, double* H9, uint8_t* ok, cudaStream_t st,
+                                   const twg_done* done);
+
 extern "C" int twg_amips_vertex_trial_energy_dev(twg_ctx* c, const double* dV, uint32_t nV, const int32_t* dTets, uint64_t nT, const int32_t* dAdjTets,
                                                  const uint64_t* dAdjOff, const int32_t* dVids, const double* dTrial, uint64_t nG, double* dE, void* stream);
 
@@ -86,23 +92,35 @@ __device__ __forceinline__ void load_tet(const double* __restrict__ V, int4 t, d
 
 // calTetQuality_AMIPS over the resident mesh (LocalOperations.cpp:862-884); t_ids == NULL: tets 0..n-1.
 // A removed tet (negative first index) gives MAX_ENERGY: the reference never evaluates those (t_is_removed).
+__device__ __forceinline__ double mesh_quality_one(const double* __restrict__ V, const int4* __restrict__ T, uint64_t ti) {
+    const int4 t = __ldg(T + ti);
+    double e = TWG_MAX_ENERGY;
+    if (t.x >= 0) {
+        double x[12];
+        load_tet(V, t, x);
+        if (tw::exact::cgal_orientation(x, x + 3, x + 6, x + 9) == 1) {
+            tw::Amips r;
+            tw::amips_eval<false>(x, r);
+            e = r.E;
+        }
+        if (isinf(e) || isnan(e) || e <= 0.0) e = TWG_MAX_ENERGY;
+    }
+    return e;
+}
 __global__ void __launch_bounds__(256, 3) mesh_quality_kernel(const double* __restrict__ V, const int4* __restrict__ T, const int32_t* __restrict__ t_ids,
                                                            uint64_t n, double* __restrict__ slim) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const int4 t = __ldg(T + (t_ids ? (uint64_t)__ldg(t_ids + i) : i));
-        double e = TWG_MAX_ENERGY;
-        if (t.x >= 0) {
-            double x[12];
-            load_tet(V, t, x);
-            if (tw::exact::cgal_orientation(x, x + 3, x + 6, x + 9) == 1) {
-                tw::Amips r;
-                tw::amips_eval<false>(x, r);
-                e = r.E;
-            }
-            if (isinf(e) || isnan(e) || e <= 0.0) e = TWG_MAX_ENERGY;
-        }
-        slim[i] = e;
-    }
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        slim[i] = mesh_quality_one(V, T, t_ids ? (uint64_t)__ldg(t_ids + i) : i);
+}
+// the tets of ONE local operation (n <= 256): ids in the kernel parameters, results straight into the mapped slab, completion
+// word raised by the kernel itself -- one driver call per host call
+struct TwgTinyTets {
+    int32_t id[256];
+};
+__global__ void __launch_bounds__(256) mesh_quality_tiny_kernel(const double* __restrict__ V, const int4* __restrict__ T, const __grid_constant__ TwgTinyTets in,
+                                                                uint32_t n, double* __restrict__ slim, twg_done done) {
+    if (threadIdx.x < n) slim[threadIdx.x] = mesh_quality_one(V, T, (uint64_t)in.id[threadIdx.x]);
+    twg_signal_done(done);
 }
 
 // calTetQuality_AD (LocalOperations.cpp:783-860). The plane through the three other vertices and the projection onto
@@ -402,10 +420,11 @@ int twg_mesh_vertex_ring_ejh(twg_mesh* m, const int32_t* v_ids, uint64_t n, doub
         char* slab;
         const size_t ib = up256(n * 4), eb = up256(n * 8), jb = up256(n * 24), hb = up256(n * 72), kb = up256(n);
         TWG_TRY(twg_fast_slab(c, ib + eb + jb + hb + kb, &slab));
-        memcpy(slab, v_ids, n * 4);
-        TWG_TRY(twg_amips_vertex_ring_ejh_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, (const int32_t*)slab, n, (double*)(slab + ib),
-                                              (double*)(slab + ib + eb), (double*)(slab + ib + eb + jb), (uint8_t*)(slab + ib + eb + jb + hb), st));
-        TWG_TRY(twg_fast_wait(c, st));
+        twg_done done;
+        TWG_TRY(twg_fast_arm(c, &done));
+        TWG_TRY(twg_amips_ring_tiny(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, v_ids, nullptr, (uint32_t)n, (double*)(slab + ib),
+                                    (double*)(slab + ib + eb), (double*)(slab + ib + eb + jb), (uint8_t*)(slab + ib + eb + jb + hb), st, &done));
+        TWG_TRY(twg_fast_spin(c, st, done.seq));
         memcpy(E, slab + ib, n * 8);
         memcpy(J3, slab + ib + eb, n * 24);
         memcpy(H9, slab + ib + eb + jb, n * 72);
@@ -535,11 +554,11 @@ int twg_mesh_vertex_trial_energy(twg_mesh* m, const int32_t* v_ids, const double
     if (n <= kFastRings && c->opt.fast_calls) {  // the step sizes of one line search: zero-copy slab
         char* slab;
         TWG_TRY(twg_fast_slab(c, ib + xb + eb, &slab));
-        memcpy(slab, v_ids, n * 4);
-        memcpy(slab + ib, xyz, n * 24);
-        TWG_TRY(twg_amips_vertex_trial_energy_dev(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, (const int32_t*)slab, (const double*)(slab + ib),
-                                                  n, (double*)(slab + ib + xb), st));
-        TWG_TRY(twg_fast_wait(c, st));
+        twg_done done;
+        TWG_TRY(twg_fast_arm(c, &done));
+        TWG_TRY(twg_amips_ring_tiny(c, m->V, m->nV, (const int32_t*)m->T, m->nT, m->adj_tets, m->adj_off, v_ids, xyz, (uint32_t)n, (double*)(slab + ib + xb), nullptr,
+                                    nullptr, nullptr, st, &done));
+        TWG_TRY(twg_fast_spin(c, st, done.seq));
         memcpy(E, slab + ib + xb, n * 8);
         return 0;
     }
@@ -587,10 +606,18 @@ static int per_tet_host(twg_mesh* m, int what, const int32_t* t_ids, uint64_t n,
         char* slab;
         const size_t ib = up256(n * 4), eb = up256(n * 8);
         TWG_TRY(twg_fast_slab(c, ib + 2 * eb, &slab));
-        memcpy(slab, t_ids, n * 4);
-        if (what == 0) TWG_LAUNCH(c, mesh_quality_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, (const int32_t*)slab, n, (double*)(slab + ib));
-        else TWG_LAUNCH(c, mesh_dihedral_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, (const int32_t*)slab, n, (double*)(slab + ib), (double*)(slab + ib + eb));
-        TWG_TRY(twg_fast_wait(c, st));
+        if (what == 0) {
+            TwgTinyTets in;
+            memcpy(in.id, t_ids, n * 4);
+            twg_done done;
+            TWG_TRY(twg_fast_arm(c, &done));
+            TWG_LAUNCH(c, mesh_quality_tiny_kernel, 1, 256, 0, st, m->V, m->T, in, (uint32_t)n, (double*)(slab + ib), done);
+            TWG_TRY(twg_fast_spin(c, st, done.seq));
+        } else {
+            memcpy(slab, t_ids, n * 4);
+            TWG_LAUNCH(c, mesh_dihedral_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, (const int32_t*)slab, n, (double*)(slab + ib), (double*)(slab + ib + eb));
+            TWG_TRY(twg_fast_wait(c, st));
+        }
         memcpy(out0, slab + ib, n * 8);
         if (what == 1) memcpy(out1, slab + ib + eb, n * 8);
         return 0;

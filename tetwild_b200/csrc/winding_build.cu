@@ -102,16 +102,46 @@ __global__ void bb_init_kernel(uint32_t* bb, size_t n) {  // min slots start at 
 struct MaxU32 {
     __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
-// bb[s][0..2] = min (encoded), bb[s][3..5] = max over the facets of segment s
-__global__ void seg_bbox_kernel(const float* __restrict__ ctr, const uint32_t* __restrict__ seg, uint32_t nF, uint32_t* bb) {
+// bb[s][0..2] = min (encoded), bb[s][3..5] = max over the facets of segment s. min / max do not depend on the order they are
+// taken in, so the reduction is free to be hierarchical: lanes of a warp that share a segment (__match_any_sync) reduce with
+// redux.sync and their leader alone goes on; while the level has at most kSegSmem segments the leaders meet in shared memory and
+// each CTA sends one atomic per segment and component to global memory. (One atomic per facet, as in the first version, spent
+// 25 of the build's 33 ms of kernel time serialised on the few boxes of the top levels: profiles/r02_launches_bench_scale0.1.txt.)
+constexpr uint32_t kSegSmem = 64;
+__global__ void __launch_bounds__(256) seg_bbox_kernel(const float* __restrict__ ctr, const uint32_t* __restrict__ seg, uint32_t nF, uint32_t nseg,
+                                                       uint32_t* bb) {
+    __shared__ uint32_t sbb[kSegSmem * 6];
+    const bool staged = nseg <= kSegSmem;
+    if (staged) {
+        for (uint32_t i = threadIdx.x; i < nseg * 6; i += blockDim.x) sbb[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+        __syncthreads();
+    }
     const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nF) return;
-    const uint32_t s = seg[f];
+    const bool in = f < nF;
+    const uint32_t s = in ? seg[f] : 0xffffffffu;  // lanes past the end form a group of their own and send nothing
+    const unsigned grp = __match_any_sync(0xffffffffu, s);
+    const bool leader = (threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const uint32_t k = enc32(ctr[3 * (size_t)f + c]);
-        atomicMin(bb + 6 * (size_t)s + c, k);
-        atomicMax(bb + 6 * (size_t)s + 3 + c, k);
+        const uint32_t k = in ? enc32(ctr[3 * (size_t)f + c]) : 0u;
+        const uint32_t lo = __reduce_min_sync(grp, k), hi = __reduce_max_sync(grp, k);
+        if (leader && in) {
+            if (staged) {
+                atomicMin(sbb + 6 * s + c, lo);
+                atomicMax(sbb + 6 * s + 3 + c, hi);
+            } else {
+                atomicMin(bb + 6 * (size_t)s + c, lo);
+                atomicMax(bb + 6 * (size_t)s + 3 + c, hi);
+            }
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < nseg * 6; i += blockDim.x) {
+            const uint32_t v = sbb[i];
+            if ((i % 6) < 3) { if (v != 0xffffffffu) atomicMin(bb + i, v); }
+            else if (v != 0u) atomicMax(bb + i, v);
+        }
     }
 }
 struct SegPlan {
@@ -454,7 +484,7 @@ int twg_winding_build_device(twg_ctx* c, const double* dV, uint32_t nV, const ui
         const uint32_t nseg = 1u << lvl, blocks = nBlkP >> lvl;
         const int cur = lvl & 1, nxt = cur ^ 1;
         TWG_LAUNCH(c, bb_init_kernel, gridof(6 * (size_t)nseg), 256, 0, st, bb, 6 * (size_t)nseg);
-        TWG_LAUNCH(c, seg_bbox_kernel, gridof(nF), 256, 0, st, (const float*)ctr, (const uint32_t*)seg, nF, bb);
+        TWG_LAUNCH(c, seg_bbox_kernel, gridof(nF), 256, 0, st, (const float*)ctr, (const uint32_t*)seg, nF, nseg, bb);
         TWG_LAUNCH(c, seg_plan_kernel, gridof(nseg), 256, 0, st, (const uint32_t*)sb[cur], (const uint32_t*)se[cur], nseg, blocks, kLeaf, (const uint32_t*)bb, plan,
                    sb[nxt], se[nxt]);
         TWG_LAUNCH(c, seg_keys_kernel, gridof(nF), 256, 0, st, (const float*)ctr, (const uint32_t*)seg, (const SegPlan*)plan, nF, fk, fv);
