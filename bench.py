@@ -634,9 +634,6 @@ def run_gpu(args, parts):
                     r["l2_bytes_per_unit_ncu"] = t["lts_bytes"] / t["units"]
             else:
                 r.update({"achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak, "note": "no L1 byte count committed for this kernel: HBM convention"})
-            for k in ("l1tex_throughput_pct", "lts_throughput_pct", "issue_active_pct", "lanes_per_inst"):
-                if k in t:
-                    r[k + "_ncu"] = t[k]
         elif bound == "latency":
             r.update({"achieved": None, "peak": None, "unit": None, "frac": None, "note": "host round trips: no device roofline applies"})
         elif bound == "fp64":
@@ -650,6 +647,13 @@ def run_gpu(args, parts):
                 r.update({"achieved": ach_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": ach_hbm / hbm_peak, "note": "no FP64 instruction count committed: HBM convention"})
         if "fp64_pipe_pct" in t:
             r["fp64_pipe_active_pct_ncu"] = t["fp64_pipe_pct"]
+        # what else the committed ncu capture of this kernel says about its limiter (percent of ncu's own peaks)
+        for k in ("l1tex_throughput_pct", "lts_throughput_pct", "dram_throughput_pct", "issue_active_pct", "lanes_per_inst", "warps_active_pct"):
+            if k in t:
+                r[k + "_ncu"] = t[k]
+        if part == "amips_ring":
+            r["note"] = ("HBM convention (the part's algorithmic traffic), but the kernel is bound by instruction issue and gather latency: see issue_active_pct_ncu, "
+                         "l1tex_throughput_pct_ncu, dram_throughput_pct_ncu and DESIGN.md 3.1")
         if extra:
             r.update(extra)
         return r

@@ -117,6 +117,10 @@ int twg_sample_triangle(twg_ctx* ctx, const double* tri9, double sampling_dist, 
  * 30-bit Morton keys (pairs-only form); sorted_xyz (nullable) = the points in sorted order (gathering form). */
 int twg_debug_sort_points(twg_ctx* ctx, const double* P, uint64_t n, const double* box6, uint32_t* perm, uint32_t* keys, double* sorted_xyz);
 
+/* measurement hook: the floor under every tiny call on this machine -- launch an empty kernel that raises the completion word in
+ * mapped host memory, spin until the host sees it; *us_per_call = host wall time per round trip over `reps` of them. */
+int twg_debug_roundtrip(twg_ctx* ctx, int reps, double* us_per_call);
+
 /* ---- roofline denominators measured on the context's device (not on the hot path; bench.py calls them once) -------- */
 /* FP64 vector pipe: DFMA microbenchmark, 2 flops per DFMA, TFLOP/s.  Copy: 128-bit grid-stride copy, read+write GB/s. */
 int twg_measure_fp64_tflops(twg_ctx* ctx, double* tflops);

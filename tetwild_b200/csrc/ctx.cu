@@ -1,5 +1,6 @@
 // ctx.cu -- context lifetime, options, per-stream lanes, scratch / pinned staging, error reporting (C ABI: include/tetwild_gpu.h).
 #include <cctype>
+#include <time.h>
 #include "common.cuh"
 
 void twg_multi_teardown(twg_ctx* c);  // multi.cu
@@ -286,6 +287,30 @@ int twg_fast_arm(twg_ctx* c, twg_done* done) {
     done->flag = (volatile uint32_t*)c->fast_slab;
     done->counter = c->fast_counter;
     done->seq = ++c->fast_seq ? c->fast_seq : ++c->fast_seq;  // never 0
+    return 0;
+}
+
+namespace {
+__global__ void fast_null_kernel(twg_done done) { twg_signal_done(done); }
+}  // namespace
+
+// the floor under every tiny call on this machine: launch an EMPTY kernel that raises the completion word, spin until the host
+// sees it (host clock around `reps` such round trips)
+int twg_debug_roundtrip(twg_ctx* c, int reps, double* us_per_call) {
+    TWG_CHECK(c, c && us_per_call && reps > 0, TWG_ERR_INVALID_ARG, "bad argument");
+    if (twg_is_multi(c)) return twg_forward0(c, twg_debug_roundtrip(c->children[0], reps, us_per_call));
+    TWG_CUDA(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->streams[0];
+    timespec t0, t1;
+    for (int i = -5; i < reps; ++i) {
+        if (i == 0) clock_gettime(CLOCK_MONOTONIC, &t0);
+        twg_done done;
+        TWG_TRY(twg_fast_arm(c, &done));
+        TWG_LAUNCH(c, fast_null_kernel, 1, 32, 0, st, done);
+        TWG_TRY(twg_fast_spin(c, st, done.seq));
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *us_per_call = ((t1.tv_sec - t0.tv_sec) * 1e6 + (t1.tv_nsec - t0.tv_nsec) * 1e-3) / reps;
     return 0;
 }
 

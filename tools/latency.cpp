@@ -76,7 +76,28 @@ int main(int argc, char** argv) {
         const double us = time_us([&] { twg_mesh_quality(m, tids.data(), n, E.data()); }, 300);
         printf("%s\"%d\": %.1f", k ? ", " : "", n, us);
     }
-    printf("}}\n");
+    printf("}, \"mesh_vertex_trial_energy_us\": {");
+    std::vector<double> X(3 * 32);
+    for (int i = 0; i < 32; ++i)
+        for (int a = 0; a < 3; ++a) X[3 * i + a] = MV[3 * (size_t)ids[i] + a] + 1e-4 * (a + 1);
+    const int nt[] = {1, 4, 16, 32};
+    for (int k = 0; k < 4; ++k) {
+        const int n = nt[k];
+        const double us = time_us([&] { twg_mesh_vertex_trial_energy(m, ids.data(), X.data(), n, E.data()); }, 300);
+        printf("%s\"%d\": %.1f", k ? ", " : "", n, us);
+    }
+    printf("}, \"nearest_us\": {");
+    std::vector<unsigned> fac(64);
+    std::vector<double> npt(3 * 64), nd2(64);
+    const int nn[] = {1, 8, 64};
+    for (int k = 0; k < 3; ++k) {
+        const int n = nn[k];
+        const double us = time_us([&] { twg_nearest(s, P.data(), n, fac.data(), npt.data(), nd2.data()); }, 300);
+        printf("%s\"%d\": %.1f", k ? ", " : "", n, us);
+    }
+    double floor_us = 0.0;
+    CK(twg_debug_roundtrip(ctx, 2000, &floor_us));
+    printf("}, \"empty_kernel_roundtrip_us\": %.2f}\n", floor_us);
     twg_mesh_destroy(m);
     twg_surface_destroy(s);
     twg_destroy(ctx);
