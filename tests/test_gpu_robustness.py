@@ -163,3 +163,35 @@ def test_own_radix_sort_is_a_stable_sort(n, bits):
     perm3, keys3, _ = c.debug_sort_points(P[np.isfinite(P).all(1)], None, want_sorted=False)
     assert (np.diff((keys3 >> (30 - bits)).astype(np.int64)) >= 0).all()
     c.close()
+
+
+def test_facet_orders_give_the_same_answers(oracle):
+    """Option surface_order picks how the facets are laid along the leaves of the implicit heap -- 0 Z curve, 1 Hilbert curve,
+    2 kd (median splits along the longest axis, aligned with the heap's node ranges; default), 3 kd with the axis chosen by child
+    surface area. The order changes the boxes, never
+    an answer: envelope decisions, face decisions and nearest distances are identical, facet ids stay the caller's."""
+    import tetwild_b200 as tw
+    V, F = synth.torus_knot(120, 24)
+    V = synth.normalise_unit_diag(V)
+    sd, eps, eps2 = synth.state_eps(1e-3)
+    P = synth.envelope_points(V, F, 60000, eps, seed=12)
+    T = synth.face_queries(V, F, 400, 0.004, eps, seed=13)
+    res = []
+    for order in (0, 1, 2, 3):
+        c = tw.Context(0)
+        c.set_option("surface_order", order)
+        S = tw.Surface(c, V, F)
+        out = S.points_out(P, eps2)
+        fo = S.faces_out(T, sd, eps2)
+        f, q, d = S.nearest(P[:20000])
+        few = S.points_out(P[:50], eps2), S.nearest(P[:50])[2]        # the tiny-call kernels walk the same structure
+        res.append((out, fo, d, f, few))
+        S.close()
+        c.close()
+    for r in res[1:]:
+        assert np.array_equal(r[0], res[0][0]) and np.array_equal(r[1], res[0][1]) and np.array_equal(r[2], res[0][2])
+        assert np.array_equal(r[4][0], res[0][0][:50]) and np.array_equal(r[4][1], res[0][2][:50])
+        assert (r[3] < len(F)).all()
+    ref = oracle.Surface(V, F).points_out(P[:5000], eps2)
+    assert np.array_equal(res[2][0][:5000], ref)
+    assert 0.05 < res[2][0].mean() < 0.95 and 0 < res[2][1].sum() < len(T)

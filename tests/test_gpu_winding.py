@@ -25,7 +25,7 @@ def test_closed_sphere_known_answers(ctx, oracle):
     assert not retried and list(keep) == [1, 1, 0, 0]
 
 
-@pytest.mark.parametrize("sort,leaf,device_build", [(1, 64, 1), (0, 64, 1), (1, 16, 1), (1, 64, 0), (0, 256, 0)])
+@pytest.mark.parametrize("sort,leaf,device_build", [(1, 32, 1), (1, 64, 1), (0, 64, 1), (1, 16, 1), (1, 32, 0), (0, 256, 0)])
 def test_vs_oracle_direct(oracle, sort, leaf, device_build):
     """query order (Morton-sorted or the caller's), leaf block size and where the hierarchy is built (device / host threads)
     are per-context options (twg_set_option); none of them may change a result beyond rounding"""

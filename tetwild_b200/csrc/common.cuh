@@ -15,22 +15,23 @@
 // Tuning knobs of one context. Defaults come from the environment ONCE, at twg_create (TWG_ENV_GROUP, TWG_SORT_BITS, ...:
 // the variable is "TWG_" + the upper-cased option name); twg_set_option changes them per context afterwards.
 struct twg_options {
-    int env_group = 64;        // queries per cooperative group of the envelope point kernel
+    int env_group = 128;       // queries per cooperative group of the envelope point kernel
     int env_policy = 1;        // round scheduling (1) or eager refill (0)
     int env_front = 32;        // frontier cap of a group: 16 / 32 / 64
     int env_quorum = 16;       // parked lanes that trigger a leaf round
     int env_top = 64;          // pair records staged in shared memory
     int env_bound = 1;         // oriented facet bound before the exact leaf routine
     int envelope_sort = 1;     // Morton-order large batches before traversal
-    int surface_order = 1;     // facet order of the envelope structure: 1 Hilbert curve, 0 Z (Morton) curve
+    int surface_order = 2;     // facet order of the envelope structure: 0 Z (Morton) curve, 1 Hilbert curve, 2 kd (splits aligned with the heap, longest centroid axis), 3 kd with the split axis chosen by child surface area
     int sort_bits = 24;        // key bits that are sorted
     int sort_curve = 0;        // query order: 0 Z (Morton) curve, 1 Hilbert curve
     long long chunk_points = 1ll << 20;  // points per staging chunk of the host entry points
     int ring_waves = 3;        // resident CTAs per SM of the one-ring kernels
+    int wide_gather = 1;       // resident-mesh quality pass: 24-byte vertices as one 16-byte + one 8-byte load instead of three 8-byte loads
     int ring_minb = 3;         // resident CTAs per SM the one-ring kernel's registers are capped for (3: 80 registers, 4: 64)
     int winding_minb = 3;
     int winding_sort = 1;
-    int winding_leaf = 64;
+    int winding_leaf = 32;
     int winding_device_build = 1;
     int amips_tma = 1;
     int nearest_mode = 1;      // 1: packets of 32 queries (+ one query per warp past the budget), 2: round-scheduled lanes, 0: per-lane descents (round 1)
@@ -126,6 +127,8 @@ int twg_ensure_scratch(twg_ctx* c, int slot, size_t bytes);
 // written into a mapped pinned slab that the kernel reads over PCIe, the results are written by the kernel straight into the
 // same slab, and completion is a word in that slab written by a one-warp kernel queued behind the work; the host spins on it.
 // twg_fast_slab returns the slab (host pointer == device pointer under unified addressing), at least `bytes` long.
+// facet order of a heap-aligned kd hierarchy (winding_build.cu); d_order: nF entries of device memory
+int twg_kd_order_device(twg_ctx* c, cudaStream_t st, const double* dV, const uint32_t* dF, uint32_t nF, uint32_t nLeafP, uint32_t stop_leaves, int sah, uint32_t* d_order);
 int twg_fast_slab(twg_ctx* c, size_t bytes, char** slab);
 int twg_fast_wait(twg_ctx* c, cudaStream_t st);
 // The same without the second launch: a kernel that takes a twg_done raises the completion word itself when its last CTA is

@@ -21,12 +21,13 @@ const OptDesc kOpts[] = {
     {"env_top", &twg_options::env_top, nullptr, 4, 512},
     {"env_bound", &twg_options::env_bound, nullptr, 0, 1},
     {"envelope_sort", &twg_options::envelope_sort, nullptr, 0, 1},
-    {"surface_order", &twg_options::surface_order, nullptr, 0, 1},
+    {"surface_order", &twg_options::surface_order, nullptr, 0, 3},
     {"sort_bits", &twg_options::sort_bits, nullptr, 8, 30},
     {"sort_curve", &twg_options::sort_curve, nullptr, 0, 1},
     {"chunk_points", nullptr, &twg_options::chunk_points, 1024, 1ll << 31},
     {"ring_waves", &twg_options::ring_waves, nullptr, 1, 32},
     {"ring_minb", &twg_options::ring_minb, nullptr, 3, 4},
+    {"wide_gather", &twg_options::wide_gather, nullptr, 0, 1},
     {"winding_minb", &twg_options::winding_minb, nullptr, 1, 8},
     {"winding_sort", &twg_options::winding_sort, nullptr, 0, 1},
     {"winding_leaf", &twg_options::winding_leaf, nullptr, 2, 4096},

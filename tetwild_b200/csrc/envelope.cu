@@ -1131,7 +1131,10 @@ __device__ __forceinline__ void env_faces_body(const SurfaceView& S, const doubl
                 uint32_t leaf_pos = 0;
                 int scan_i = 0;
                 for (;;) {
-                    if (__ballot_sync(full, stage != DONE) == 0u || flag[wib]) break;
+                    // the flag is read BEFORE the vote: a lane that leaves the vote early may already be raising it in its SCAN stage
+                    // below (racecheck, round 2), and lanes that disagreed about it would leave the loop at different rounds
+                    const int stop = flag[wib];
+                    if (__ballot_sync(full, stage != DONE) == 0u || __any_sync(full, stop != 0)) break;
                     // fixed order SCAN -> FETCH -> LEAF: scanning lanes find their next candidate and fetching lanes their next
                     // sample first (cheap stages, subsets of the warp), so that the expensive exact test then runs ONCE for
                     // every lane that has a facet to test -- hint facets and scan candidates in the same round

@@ -92,12 +92,26 @@ __device__ __forceinline__ void load_tet(const double* __restrict__ V, int4 t, d
 
 // calTetQuality_AMIPS over the resident mesh (LocalOperations.cpp:862-884); t_ids == NULL: tets 0..n-1.
 // A removed tet (negative first index) gives MAX_ENERGY: the reference never evaluates those (t_is_removed).
+// a 24-byte vertex with one 16-byte and one 8-byte load (whichever half is 16-byte aligned), never reading outside the vertex:
+// two L1 wavefronts per lane instead of three (ncu r02: the quality pass keeps L1 77 % busy at 24 % issue utilisation)
+__device__ __forceinline__ void load_tet_wide(const double* __restrict__ V, int4 t, double* x) {
+    const int32_t v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double* p = V + 3 * (size_t)v[j];
+        const bool odd = (reinterpret_cast<uintptr_t>(p) & 8u) != 0;
+        const double2 a = __ldg(reinterpret_cast<const double2*>(p + (odd ? 1 : 0)));
+        const double b = __ldg(p + (odd ? 0 : 2));
+        x[3 * j] = odd ? b : a.x; x[3 * j + 1] = odd ? a.x : a.y; x[3 * j + 2] = odd ? a.y : b;
+    }
+}
+template <bool WIDE = false>
 __device__ __forceinline__ double mesh_quality_one(const double* __restrict__ V, const int4* __restrict__ T, uint64_t ti) {
     const int4 t = __ldg(T + ti);
     double e = TWG_MAX_ENERGY;
     if (t.x >= 0) {
         double x[12];
-        load_tet(V, t, x);
+        if (WIDE) load_tet_wide(V, t, x); else load_tet(V, t, x);
         if (tw::exact::cgal_orientation(x, x + 3, x + 6, x + 9) == 1) {
             tw::Amips r;
             tw::amips_eval<false>(x, r);
@@ -107,10 +121,11 @@ __device__ __forceinline__ double mesh_quality_one(const double* __restrict__ V,
     }
     return e;
 }
+template <bool WIDE>
 __global__ void __launch_bounds__(256, 3) mesh_quality_kernel(const double* __restrict__ V, const int4* __restrict__ T, const int32_t* __restrict__ t_ids,
                                                            uint64_t n, double* __restrict__ slim) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        slim[i] = mesh_quality_one(V, T, t_ids ? (uint64_t)__ldg(t_ids + i) : i);
+        slim[i] = mesh_quality_one<WIDE>(V, T, t_ids ? (uint64_t)__ldg(t_ids + i) : i);
 }
 // the tets of ONE local operation (n <= 256): ids in the kernel parameters, results straight into the mapped slab, completion
 // word raised by the kernel itself -- one driver call per host call
@@ -628,7 +643,8 @@ static int per_tet_host(twg_mesh* m, int what, const int32_t* t_ids, uint64_t n,
     if (t_ids) TWG_TRY(stage(c, o, t_ids, n, &dI));
     TWG_TRY(stage(c, o, (const double*)nullptr, n, &d0));
     TWG_TRY(stage(c, o, (const double*)nullptr, n, &d1));
-    if (what == 0) TWG_LAUNCH(c, mesh_quality_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, dI, n, d0);
+    if (what == 0 && c->opt.wide_gather) TWG_LAUNCH(c, mesh_quality_kernel<true>, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, dI, n, d0);
+    else if (what == 0) TWG_LAUNCH(c, mesh_quality_kernel<false>, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, dI, n, d0);
     else TWG_LAUNCH(c, mesh_dihedral_kernel, grid_for(c, n, 256, 8), 256, 0, st, m->V, m->T, dI, n, d0, d1);
     TWG_CUDA(c, cudaMemcpyAsync(out0, d0, n * 8, cudaMemcpyDeviceToHost, st));
     if (what == 1) TWG_CUDA(c, cudaMemcpyAsync(out1, d1, n * 8, cudaMemcpyDeviceToHost, st));
@@ -655,7 +671,8 @@ int twg_mesh_quality_dev(twg_mesh* m, const int32_t* dTids, uint64_t n, double* 
     if (!dTids) n = m->nT;
     if (n == 0) return 0;
     TWG_CUDA(c, cudaSetDevice(c->device));
-    TWG_LAUNCH(c, mesh_quality_kernel, grid_for(c, n, 256, 8), 256, 0, stream ? (cudaStream_t)stream : c->streams[0], m->V, m->T, dTids, n, dSlim);
+    if (c->opt.wide_gather) TWG_LAUNCH(c, mesh_quality_kernel<true>, grid_for(c, n, 256, 8), 256, 0, stream ? (cudaStream_t)stream : c->streams[0], m->V, m->T, dTids, n, dSlim);
+    else TWG_LAUNCH(c, mesh_quality_kernel<false>, grid_for(c, n, 256, 8), 256, 0, stream ? (cudaStream_t)stream : c->streams[0], m->V, m->T, dTids, n, dSlim);
     return 0;
 }
 int twg_mesh_dihedral_dev(twg_mesh* m, const int32_t* dTids, uint64_t n, double* dMin, double* dMax, void* stream) {

@@ -212,6 +212,11 @@ int build(twg_ctx* c, const double* dV, uint32_t nV, const uint32_t* dF, uint32_
     B_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
     B_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, vals, vals2, (int)nF, 0, 63, st));
     c->launches += 4;  // cub: histogram + onesweep passes (approximate, library kernels)
+    if (c->opt.surface_order >= 2 && lp > 8) {
+        // kd order (winding_build.cu): count-balanced median splits along the longest axis, aligned with the heap's node ranges
+        const int krc = twg_kd_order_device(c, st, dV, dF, nF, lp, 8u, c->opt.surface_order >= 3 ? 1 : 0, vals2);
+        if (krc != 0) return fail(krc);
+    }
     leaf_kernel<<<(lp + 127) / 128, 128, 0, st>>>(dV, dF, vals2, nF, lp, s->tris, s->triV, s->pairs, s->tb);
     c->launches++;
     for (uint32_t first = lp / 2; first >= 2; first >>= 1) {

@@ -191,6 +191,96 @@ __global__ void seg_assign_kernel(const uint32_t* __restrict__ sorted_f, const S
     const uint32_t s = seg[f];
     seg[f] = 2u * s + (p >= plan[s].mid ? 1u : 0u);
 }
+// ---- split axis by surface area (twg_kd_order_device, `sah` form): the facets of a node, sorted along axis a and cut at the heap's
+// position, give two child boxes; the axis with the smallest  area(L) nL + area(R) nR  wins (the counts are the same for all axes)
+__global__ void fbox_kernel(const double* __restrict__ V, const uint32_t* __restrict__ F, uint32_t nF, float* fbox) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double a = V[3 * (size_t)F[3 * (size_t)f] + c], b = V[3 * (size_t)F[3 * (size_t)f + 1] + c], d = V[3 * (size_t)F[3 * (size_t)f + 2] + c];
+        fbox[6 * (size_t)f + c] = __double2float_rd(fmin(a, fmin(b, d)));
+        fbox[6 * (size_t)f + 3 + c] = __double2float_ru(fmax(a, fmax(b, d)));
+    }
+}
+// cb[2 s + child][0..2] = min, [3..5] = max (encoded) over the facet boxes of that child; same hierarchical reduction as seg_bbox_kernel
+__global__ void __launch_bounds__(256) child_box_kernel(const float* __restrict__ fbox, const uint32_t* __restrict__ sorted_f, const uint32_t* __restrict__ seg,
+                                                        const SegPlan* __restrict__ plan, uint32_t nF, uint32_t ngrp, uint32_t* cb) {
+    __shared__ uint32_t sbb[kSegSmem * 6];
+    const bool staged = ngrp <= kSegSmem;
+    if (staged) {
+        for (uint32_t i = threadIdx.x; i < ngrp * 6; i += blockDim.x) sbb[i] = (i % 6) < 3 ? 0xffffffffu : 0u;
+        __syncthreads();
+    }
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = p < nF;
+    uint32_t f = 0, g = 0xffffffffu;
+    if (in) {
+        f = sorted_f[p];
+        const uint32_t s = seg[f];
+        g = 2u * s + (p >= plan[s].mid ? 1u : 0u);
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, g);
+    const bool leader = (threadIdx.x & 31) == (unsigned)(__ffs(grp) - 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint32_t klo = in ? enc32(fbox[6 * (size_t)f + c]) : 0xffffffffu, khi = in ? enc32(fbox[6 * (size_t)f + 3 + c]) : 0u;
+        const uint32_t lo = __reduce_min_sync(grp, klo), hi = __reduce_max_sync(grp, khi);
+        if (leader && in) {
+            uint32_t* dst = staged ? sbb : cb;
+            atomicMin(dst + 6 * (size_t)g + c, lo);
+            atomicMax(dst + 6 * (size_t)g + 3 + c, hi);
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < ngrp * 6; i += blockDim.x) {
+            const uint32_t v = sbb[i];
+            if ((i % 6) < 3) { if (v != 0xffffffffu) atomicMin(cb + i, v); }
+            else if (v != 0u) atomicMax(cb + i, v);
+        }
+    }
+}
+__global__ void axis_cost_kernel(const uint32_t* __restrict__ cb, const SegPlan* __restrict__ plan, const uint32_t* __restrict__ sb, const uint32_t* __restrict__ se,
+                                 uint32_t nseg, float* cost) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg) return;
+    float total = 0.f;
+    for (int child = 0; child < 2; ++child) {
+        const uint32_t n = child == 0 ? plan[s].mid - sb[s] : se[s] - plan[s].mid;
+        if (n == 0) continue;
+        const uint32_t* b = cb + 6 * (size_t)(2 * s + child);
+        const float dx = dec32(b[3]) - dec32(b[0]), dy = dec32(b[4]) - dec32(b[1]), dz = dec32(b[5]) - dec32(b[2]);
+        total += (dx * dy + dy * dz + dz * dx) * (float)n;
+    }
+    cost[s] = total;
+}
+// ax[s] = the cheapest of the three axes (ties: the lower axis), for segments that are split at all
+__global__ void axis_pick_kernel(const float* __restrict__ cost3, uint32_t nseg, SegPlan* plan) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseg || plan[s].ax < 0) return;
+    int best = 0;
+    if (cost3[nseg + s] < cost3[best * (size_t)nseg + s]) best = 1;
+    if (cost3[2 * (size_t)nseg + s] < cost3[best * (size_t)nseg + s]) best = 2;
+    plan[s].ax = best;
+}
+__global__ void axis_keys_kernel(const float* __restrict__ ctr, const uint32_t* __restrict__ seg, const SegPlan* __restrict__ plan, uint32_t nF, int ax,
+                                 unsigned long long* keys, uint32_t* vals) {
+    const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    const uint32_t s = seg[f];
+    keys[f] = ((unsigned long long)s << 32) | (plan[s].ax >= 0 ? (unsigned long long)enc32(ctr[3 * (size_t)f + ax]) : 0ull);
+    vals[f] = f;
+}
+// the order of the level: position p takes the facet the winning axis of its segment put there (a segment is the same range of
+// positions under all three sorts)
+__global__ void axis_merge_kernel(const uint32_t* __restrict__ o0, const uint32_t* __restrict__ o1, const uint32_t* __restrict__ o2, const uint32_t* __restrict__ seg,
+                                  const SegPlan* __restrict__ plan, uint32_t nF, uint32_t* order) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nF) return;
+    const int ax = plan[seg[o0[p]]].ax;
+    order[p] = ax == 1 ? o1[p] : (ax == 2 ? o2[p] : o0[p]);
+}
 __global__ void block_keys_kernel(const uint32_t* __restrict__ sorted_f, uint32_t nF, uint32_t kLeaf, unsigned long long* keys, uint32_t* vals) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= nF) return;
@@ -426,6 +516,75 @@ static int sort_pairs(twg_ctx* c, Arena& A, cudaStream_t st, K*& keys, K*& keys_
     c->launches += 2 + (end_bit - begin_bit + 7) / 8;
     std::swap(keys, keys_alt);
     std::swap(vals, vals_alt);
+    return 0;
+}
+
+// Facet order of a count-balanced kd hierarchy whose splits sit exactly where an IMPLICIT HEAP over nLeafP one-facet leaves puts
+// them (the surface structure of surface.cu): the facets of a heap node of `blocks` leaves go, sorted along the longest axis of
+// their centroid box, blocks / 2 to the left child and the rest to the right one, level by level until a node has `stop_leaves`
+// leaves (one 8-wide step of the traversal: the order inside does not change any box above the facets). Same level kernels as the
+// winding hierarchy below (leaf size 1); d_order[p] = facet at leaf p. Deterministic: ties keep their previous order (stable sort).
+int twg_kd_order_device(twg_ctx* c, cudaStream_t st, const double* dV, const uint32_t* dF, uint32_t nF, uint32_t nLeafP, uint32_t stop_leaves, int sah,
+                        uint32_t* d_order) {
+    Arena A(st);
+    float* ctr;
+    uint32_t *seg, *fv, *fv2, *sb[2], *se[2], *bb;
+    unsigned long long *fk, *fk2;
+    SegPlan* plan;
+    if (stop_leaves < 1) stop_leaves = 1;
+    uint32_t max_seg = nLeafP / stop_leaves;
+    if (max_seg < 1) max_seg = 1;
+    WB_CUDA(A.get(&ctr, 3 * (size_t)nF)); WB_CUDA(A.get(&seg, nF)); WB_CUDA(A.get(&fv, nF)); WB_CUDA(A.get(&fv2, nF));
+    WB_CUDA(A.get(&fk, nF)); WB_CUDA(A.get(&fk2, nF));
+    for (int k = 0; k < 2; ++k) { WB_CUDA(A.get(&sb[k], (size_t)max_seg * 2)); WB_CUDA(A.get(&se[k], (size_t)max_seg * 2)); }
+    WB_CUDA(A.get(&bb, 6 * (size_t)max_seg)); WB_CUDA(A.get(&plan, max_seg));
+    float *fbox = nullptr, *cost3 = nullptr;
+    uint32_t *cb = nullptr, *oax[3] = {nullptr, nullptr, nullptr};
+    if (sah) {
+        WB_CUDA(A.get(&fbox, 6 * (size_t)nF)); WB_CUDA(A.get(&cost3, 3 * (size_t)max_seg)); WB_CUDA(A.get(&cb, 12 * (size_t)max_seg));
+        for (int ax = 0; ax < 3; ++ax) WB_CUDA(A.get(&oax[ax], nF));
+        TWG_LAUNCH(c, fbox_kernel, gridof(nF), 256, 0, st, dV, dF, nF, fbox);
+    }
+    TWG_LAUNCH(c, ctr_kernel, gridof(nF), 256, 0, st, dV, dF, nF, ctr);
+    WB_CUDA(cudaMemsetAsync(seg, 0, sizeof(uint32_t) * (size_t)nF, st));
+    {
+        const uint32_t be[2] = {0u, nF};
+        WB_CUDA(cudaMemcpyAsync(sb[0], &be[0], 4, cudaMemcpyHostToDevice, st));
+        WB_CUDA(cudaMemcpyAsync(se[0], &be[1], 4, cudaMemcpyHostToDevice, st));
+        WB_CUDA(cudaStreamSynchronize(st));  // `be` lives on this stack frame
+    }
+    TWG_LAUNCH(c, iota_kernel, gridof(nF), 256, 0, st, fv, nF);
+    for (int lvl = 0; (nLeafP >> lvl) > stop_leaves; ++lvl) {
+        const uint32_t nseg = 1u << lvl, blocks = nLeafP >> lvl;
+        const int cur = lvl & 1, nxt = cur ^ 1;
+        TWG_LAUNCH(c, bb_init_kernel, gridof(6 * (size_t)nseg), 256, 0, st, bb, 6 * (size_t)nseg);
+        TWG_LAUNCH(c, seg_bbox_kernel, gridof(nF), 256, 0, st, (const float*)ctr, (const uint32_t*)seg, nF, nseg, bb);
+        TWG_LAUNCH(c, seg_plan_kernel, gridof(nseg), 256, 0, st, (const uint32_t*)sb[cur], (const uint32_t*)se[cur], nseg, blocks, 1u, (const uint32_t*)bb, plan, sb[nxt],
+                   se[nxt]);
+        if (sah) {
+            // three sorts, two child boxes each, cheapest axis per segment; ties inside a sort keep the facet id order (keys are
+            // rebuilt from the ids, values start as iota: the result does not depend on the previous level's order)
+            for (int ax = 0; ax < 3; ++ax) {
+                TWG_LAUNCH(c, axis_keys_kernel, gridof(nF), 256, 0, st, (const float*)ctr, (const uint32_t*)seg, (const SegPlan*)plan, nF, ax, fk, fv);
+                TWG_TRY(sort_pairs(c, A, st, fk, fk2, fv, fv2, nF, 0, 32 + (lvl > 0 ? lvl : 1)));
+                WB_CUDA(cudaMemcpyAsync(oax[ax], fv, sizeof(uint32_t) * (size_t)nF, cudaMemcpyDeviceToDevice, st));
+                TWG_LAUNCH(c, bb_init_kernel, gridof(12 * (size_t)nseg), 256, 0, st, cb, 12 * (size_t)nseg);
+                TWG_LAUNCH(c, child_box_kernel, gridof(nF), 256, 0, st, (const float*)fbox, (const uint32_t*)oax[ax], (const uint32_t*)seg, (const SegPlan*)plan, nF, 2 * nseg,
+                           cb);
+                TWG_LAUNCH(c, axis_cost_kernel, gridof(nseg), 256, 0, st, (const uint32_t*)cb, (const SegPlan*)plan, (const uint32_t*)sb[cur], (const uint32_t*)se[cur], nseg,
+                           cost3 + (size_t)ax * nseg);
+            }
+            TWG_LAUNCH(c, axis_pick_kernel, gridof(nseg), 256, 0, st, (const float*)cost3, nseg, plan);
+            TWG_LAUNCH(c, axis_merge_kernel, gridof(nF), 256, 0, st, (const uint32_t*)oax[0], (const uint32_t*)oax[1], (const uint32_t*)oax[2], (const uint32_t*)seg,
+                       (const SegPlan*)plan, nF, fv);
+        } else {
+            TWG_LAUNCH(c, seg_keys_kernel, gridof(nF), 256, 0, st, (const float*)ctr, (const uint32_t*)seg, (const SegPlan*)plan, nF, fk, fv);
+            TWG_TRY(sort_pairs(c, A, st, fk, fk2, fv, fv2, nF, 0, 32 + (lvl > 0 ? lvl : 1)));
+        }
+        TWG_LAUNCH(c, seg_assign_kernel, gridof(nF), 256, 0, st, (const uint32_t*)fv, (const SegPlan*)plan, nF, seg);
+    }
+    WB_CUDA(cudaMemcpyAsync(d_order, fv, sizeof(uint32_t) * (size_t)nF, cudaMemcpyDeviceToDevice, st));
+    WB_CUDA(cudaStreamSynchronize(st));  // the arena frees behind the copy (stream-ordered); callers may use d_order on any stream
     return 0;
 }
 
