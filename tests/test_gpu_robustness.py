@@ -113,9 +113,9 @@ def test_out_of_range_indices_are_refused_not_dereferenced(ctx):
 
 def test_options_are_per_context():
     a, b = tw.Context(0), tw.Context(0)
-    a.set_option("env_group", 128)
+    a.set_option("env_group", 32)
     a.set_option("sort_bits", 99)          # clamped
-    assert a.get_option("env_group") == 128 and b.get_option("env_group") == 64
+    assert a.get_option("env_group") == 32 and b.get_option("env_group") == 128
     assert a.get_option("sort_bits") == 30
     with pytest.raises(tw.TetWildGPUError):
         a.set_option("no_such_option", 1)
