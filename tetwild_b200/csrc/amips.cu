@@ -13,7 +13,9 @@
 //   amips_quality_kernel indexed gather (int4 tet load + 4 vertex gathers), exact orientation gate.
 //   amips_ring_kernel    one warp per one-ring, lanes over member tets, software-pipelined over the warp's rings
 //                        (index chain of later rings in flight), 10 sums reduced through a shared-memory transpose.
-//                        Gather-latency bound.
+//                        Bound by instruction issue + gather latency (0.40 of the HBM peak; five other shapes measured, see below).
+//   amips_ring_tiny_kernel the same body for ONE un-batched call (<= 32 rings): vertex ids / trial positions in the kernel
+//                        parameters, completion word raised by the kernel (common.cuh::twg_signal_done).
 #include "common.cuh"
 
 namespace {
