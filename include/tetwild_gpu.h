@@ -67,7 +67,7 @@ int twg_synchronize(twg_ctx* ctx);
 uint64_t twg_launch_count(const twg_ctx* ctx);  /* kernels launched by this context so far */
 const char* twg_version(void);
 /* Tuning knobs, per context (defaults: environment variable TWG_<NAME> read once at twg_create). Names: env_group, env_policy,
- * env_front, env_quorum, env_top, env_bound, envelope_sort, surface_order, sort_bits, sort_curve, chunk_points, ring_waves, ring_minb, wide_gather, winding_minb, winding_sort,
+ * env_front, env_quorum, env_top, env_bound, envelope_sort, surface_order, sort_bits, sort_curve, nearest_curve, chunk_points, ring_waves, ring_minb, wide_gather, winding_minb, winding_sort,
  * winding_leaf, winding_device_build, amips_tma, nearest_mode, nearest_group, nearest_budget, fast_calls, trace. Values are clamped to their valid range. */
 int twg_set_option(twg_ctx* ctx, const char* name, double value);
 int twg_get_option(const twg_ctx* ctx, const char* name, double* value);

@@ -24,7 +24,8 @@ struct twg_options {
     int envelope_sort = 1;     // Morton-order large batches before traversal
     int surface_order = 2;     // facet order of the envelope structure: 0 Z (Morton) curve, 1 Hilbert curve, 2 kd (splits aligned with the heap, longest centroid axis), 3 kd with the split axis chosen by child surface area
     int sort_bits = 24;        // key bits that are sorted
-    int sort_curve = 0;        // query order: 0 Z (Morton) curve, 1 Hilbert curve
+    int sort_curve = 0;        // query order of the envelope / winding batches: 0 Z (Morton) curve, 1 Hilbert curve
+    int nearest_curve = 1;     // query order of the nearest-facet batches (Hilbert: 24.9 -> 22.7 ms per 10 M points; the envelope test prefers Z: 1.75 vs 1.79 ms)
     long long chunk_points = 1ll << 20;  // points per staging chunk of the host entry points
     int ring_waves = 3;        // resident CTAs per SM of the one-ring kernels
     int wide_gather = 1;       // resident-mesh quality pass: 24-byte vertices as one 16-byte + one 8-byte load instead of three 8-byte loads
@@ -163,7 +164,7 @@ int twg_get_lane(twg_ctx* c, cudaStream_t st, twg_lane** out);
 // marks the lane busy until everything queued on its stream so far has completed (call after the last launch of an entry point)
 int twg_lane_mark(twg_ctx* c, twg_lane* lane);
 int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box = nullptr,
-                    const double** sorted_out = nullptr, const uint32_t** keys_out_dbg = nullptr);
+                    const double** sorted_out = nullptr, const uint32_t** keys_out_dbg = nullptr, int curve = -1 /* -1: option sort_curve */);
 inline bool twg_is_multi(const twg_ctx* c) { return c && !c->children.empty(); }
 // multi.cu: fn(k, child_k) on every device's own host thread, concurrently; first non-zero return code wins
 int twg_multi_run(twg_ctx* c, const std::function<int(int, twg_ctx*)>& fn);

@@ -24,6 +24,7 @@ const OptDesc kOpts[] = {
     {"surface_order", &twg_options::surface_order, nullptr, 0, 3},
     {"sort_bits", &twg_options::sort_bits, nullptr, 8, 30},
     {"sort_curve", &twg_options::sort_curve, nullptr, 0, 1},
+    {"nearest_curve", &twg_options::nearest_curve, nullptr, 0, 1},
     {"chunk_points", nullptr, &twg_options::chunk_points, 1024, 1ll << 31},
     {"ring_waves", &twg_options::ring_waves, nullptr, 1, 32},
     {"ring_minb", &twg_options::ring_minb, nullptr, 3, 4},

@@ -1274,7 +1274,7 @@ int twg_nearest_dev(twg_surface* s, const double* dP, uint64_t n, uint32_t* dFac
     const uint32_t* perm = nullptr;
     const double* Pq = nullptr;
     const bool sorted = n >= TWG_SORT_MIN && c->opt.envelope_sort;
-    if (sorted) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box, &Pq));
+    if (sorted) TWG_TRY(twg_sort_points(c, lane, st, dP, n, &perm, s->sort_box, &Pq, nullptr, c->opt.nearest_curve));
     TWG_CUDA(c, cudaMemsetAsync(lane->counters, 0, sizeof(unsigned long long), st));
     if (sorted && c->opt.nearest_mode == 2 && s->nLeafP >= 8) {  // round-scheduled lanes (form 3)
         const int group = c->opt.nearest_group;

@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(kSortThreads, 4) qs_scatter_kernel(const uint3
 // instead of reducing the batch's own bounding box first -- the surface's box is what matters to both traversals.
 // sorted_out (optional): the points themselves in sorted order (gathered by the last pass).
 int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* dP, uint64_t n, const uint32_t** perm_out, const double* known_box,
-                    const double** sorted_out, const uint32_t** keys_out_dbg) {
+                    const double** sorted_out, const uint32_t** keys_out_dbg, int curve) {
+    if (curve < 0) curve = c->opt.sort_curve;
     TWG_CHECK(c, n <= 0x7fffffffull, TWG_ERR_INVALID_ARG, "at most 2^31-1 queries per device call (the host entry points chunk larger batches)");
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     // The keys are 30-bit Morton codes; only the top `bits` are sorted (stable): 24 bits = a 256^3 grid over the surface's
@@ -335,7 +336,7 @@ int twg_sort_points(twg_ctx* c, twg_lane* lane, cudaStream_t st, const double* d
         const int width = (bits - 8 * p) < 8 ? (bits - 8 * p) : 8;
         dg.mask = (1u << width) - 1u;
         if (p == 0)
-            TWG_LAUNCH(c, qs_keys_hist_kernel, ntiles, kSortThreads, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, kbuf[0], hist, ntiles, dg, c->opt.sort_curve);
+            TWG_LAUNCH(c, qs_keys_hist_kernel, ntiles, kSortThreads, 0, st, dP, n, known_box ? (const unsigned long long*)nullptr : bounds, known, kbuf[0], hist, ntiles, dg, curve);
         else
             TWG_LAUNCH(c, qs_tile_hist_kernel, ntiles, kSortThreads, 0, st, (const uint32_t*)kbuf[cur], n, hist, ntiles, dg);
         TWG_LAUNCH(c, qs_row_scan_kernel, 256, 256, 0, st, hist, ntiles, total);
